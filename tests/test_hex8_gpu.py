@@ -1,0 +1,162 @@
+"""GPU parity of the matrix-free hex8 operator, the PCG state solve, objective and sensitivities
+against the CPU oracle (oracle/topopt_oracle.py).  All calls go through the C-ABI (ctypes)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "appendix_c.json")))
+
+
+def densities(kind, g, rng):
+    if kind == "uniform":
+        return np.full(g.nel, 0.12)
+    if kind == "random":
+        return rng.uniform(0.0, 1.0, g.nel)
+    # checker of 4^3 blocks, high contrast
+    i, j, k = np.meshgrid(np.arange(g.nex), np.arange(g.ney), np.arange(g.nez), indexing="ij")
+    chk = (((i // 4) + (j // 4) + (k // 4)) % 2).astype(float)
+    return chk.transpose(2, 1, 0).ravel()
+
+
+@pytest.mark.parametrize("shape,xc", [((9, 5, 5), (0, 2, 0, 1, 0, 1)), ((34, 21, 13), (0, 2, 0, 1, 0, 1)),
+                                      ((65, 33, 33), (0, 2, 0, 1, 0, 1)), ((20, 12, 9), (0, 1.3, 0, 0.7, 0, 0.45))])
+def test_ke_matches_oracle(oracle, shape, xc):
+    from topopt_in_petsc_b200 import Context, LinearElasticity
+    g = oracle.Grid(*shape, xc=xc)
+    ctx = Context(*shape, xc=xc)
+    phys = LinearElasticity(ctx, nu=0.3)
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    assert np.abs(phys.GetKE() - KE).max() <= 1e-15 * np.abs(KE).max() * 24
+    phys.close(); ctx.close()
+
+
+@pytest.mark.parametrize("shape,xc", [((9, 5, 5), (0, 2, 0, 1, 0, 1)), ((34, 21, 13), (0, 2, 0, 1, 0, 1)),
+                                      ((65, 33, 33), (0, 2, 0, 1, 0, 1)), ((20, 12, 9), (0, 1.3, 0, 0.7, 0, 0.45))])
+@pytest.mark.parametrize("dens", ["uniform", "random", "checker"])
+def test_spmv_parity(oracle, shape, xc, dens):
+    """y = N.(K(N.u)) + (1-N).u  vs the oracle; every SpMV kernel; tolerance 1e-12 relative (fp64)."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    rng = np.random.default_rng(1234)
+    g = oracle.Grid(*shape, xc=xc)
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N, _ = oracle.cantilever_bc_load(g)
+    x = densities(dens, g, rng)
+    E = oracle.simp_modulus(x, 1e-9, 1.0, 3.0)
+    u = rng.uniform(-1, 1, g.ndof)
+    yref = oracle.spmv_matrix_free(g, KE, E, N, u)
+    ctx = Context(*shape, xc=xc)
+    assert ctx.nel == g.nel and ctx.ndof == g.ndof  # bit-exact counts (TopOpt.cc:172-175)
+    scale = np.abs(yref).max()
+    for kernel in (1, 2, 3):
+        phys = LinearElasticity(ctx, nu=0.3, opts=solver_opts(spmv_kernel=kernel))
+        phys.SetDensity(x, 1e-9, 1.0, 3.0)
+        y = phys.SpMV(u)
+        assert np.abs(y - yref).max() <= 1e-12 * scale, (kernel, np.abs(y - yref).max() / scale)
+        d = phys.Diag()
+        K = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N)
+        assert np.abs(d - K.diagonal()).max() <= 1e-13 * np.abs(K.diagonal()).max()
+        phys.close()
+    ctx.close()
+
+
+def test_spmv_linearity_large():
+    """Size-independent property at a larger grid: A(au+bv) = aAu + bAv, and A symmetric: v.Au = u.Av."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity
+    rng = np.random.default_rng(7)
+    shape = (129, 65, 65)
+    ctx = Context(*shape)
+    phys = LinearElasticity(ctx)
+    x = rng.uniform(0, 1, ctx.nel)
+    phys.SetDensity(x, 1e-9, 1.0, 3.0)
+    u, v = rng.uniform(-1, 1, ctx.ndof), rng.uniform(-1, 1, ctx.ndof)
+    Au, Av = phys.SpMV(u), phys.SpMV(v)
+    Aw = phys.SpMV(0.3 * u - 1.7 * v)
+    s = np.abs(Au).max()
+    assert np.abs(Aw - (0.3 * Au - 1.7 * Av)).max() <= 1e-12 * s
+    assert abs(v @ Au - u @ Av) <= 1e-11 * abs(v @ Au)
+    phys.close(); ctx.close()
+
+
+@pytest.mark.parametrize("shape,key", [((49, 25, 25), "48x24x24"), ((65, 33, 33), "64x32x32")])
+def test_iteration1_compliance_golden(shape, key):
+    """Iteration-1 compliance of the reference cantilever at uniform x=0.12.
+    Solver tolerance 1e-10 -> fx within 1e-8 relative (fx error is second order in the residual)."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    ctx = Context(*shape)
+    phys = LinearElasticity(ctx, opts=solver_opts(rtol=1e-10, maxits=20000))
+    x = np.full(ctx.nel, 0.12)
+    dfdx, dgdx = np.empty(ctx.nel), np.empty(ctx.nel)
+    fx, gx = phys.ComputeObjectiveConstraintsSensitivities(dfdx, dgdx, x, 1e-9, 1.0, 3.0, 0.12)
+    gold = GOLD[key]
+    assert abs(fx - gold["fx"]) <= 1e-8 * gold["fx"]
+    assert abs(gx) < 1e-12
+    assert abs(dfdx.sum() - gold["sum_dfdx"]) <= 1e-7 * abs(gold["sum_dfdx"])
+    assert abs(dfdx.min() - gold["min_dfdx"]) <= 1e-6 * abs(gold["min_dfdx"])
+    assert np.allclose(dgdx, 1.0 / ctx.nel)
+    rhs = phys.GetRHS()
+    assert abs(np.linalg.norm(rhs) - gold["rhs_norm"]) <= 1e-12 and abs(rhs.sum() - gold["rhs_sum"]) <= 1e-15
+    U = phys.GetStateField()
+    nxn = shape[0]
+    assert abs(U[3 * (nxn - 1) + 2] - gold["uz_tip"]) <= 1e-6 * abs(gold["uz_tip"])
+    st = phys.stats()
+    assert st.rel_residual <= 1e-10 and st.iterations > 0
+    phys.close(); ctx.close()
+
+
+@pytest.mark.parametrize("dens", ["random", "checker"])
+def test_solve_obj_sens_vs_oracle(oracle, dens):
+    """State solve + objective + sensitivities on a non-uniform design vs the oracle (tight solves)."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    rng = np.random.default_rng(3)
+    shape = (25, 13, 13)
+    g = oracle.Grid(*shape)
+    x = densities(dens, g, rng)
+    if dens == "random":
+        x = 0.05 + 0.9 * x
+    else:
+        x = 0.001 + 0.998 * x
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N, RHS = oracle.cantilever_bc_load(g)
+    K = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N)
+    import scipy.sparse.linalg as spla
+    U = spla.spsolve(K.tocsc(), N * RHS)
+    fx0, gx0, df0, dg0 = oracle.objective_sens(g, KE, U, x, 1e-9, 1.0, 3.0, 0.12)
+    ctx = Context(*shape)
+    phys = LinearElasticity(ctx, opts=solver_opts(rtol=1e-11, maxits=50000))
+    dfdx, dgdx = np.empty(ctx.nel), np.empty(ctx.nel)
+    fx, gx = phys.ComputeObjectiveConstraintsSensitivities(dfdx, dgdx, x, 1e-9, 1.0, 3.0, 0.12)
+    assert abs(fx - fx0) <= 1e-7 * abs(fx0)
+    assert abs(gx - gx0) <= 1e-13
+    assert np.abs(dfdx - df0).max() <= 1e-6 * np.abs(df0).max()
+    Ug = phys.GetStateField()
+    assert np.abs(Ug - U).max() <= 1e-6 * np.abs(U).max()
+    # warm start: a second solve from the converged state needs (almost) no iterations
+    st = phys.SolveState(x, 1e-9, 1.0, 3.0)
+    assert st.iterations <= 1
+    phys.close(); ctx.close()
+
+
+def test_custom_bc_load(oracle):
+    """Generalised BC/load entry point: clamp the z=0 plane, point load at a top corner."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    import scipy.sparse.linalg as spla
+    shape = (13, 9, 11)
+    g = oracle.Grid(*shape)
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N = np.ones(g.ndof)
+    N[:3 * g.nxn * g.nyn] = 0.0
+    RHS = np.zeros(g.ndof)
+    RHS[3 * g.node_id(g.nxn - 1, g.nyn - 1, g.nzn - 1) + 1] = 0.5
+    x = np.full(g.nel, 0.4)
+    K = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N)
+    U = spla.spsolve(K.tocsc(), N * RHS)
+    ctx = Context(*shape)
+    phys = LinearElasticity(ctx, opts=solver_opts(rtol=1e-12, maxits=50000))
+    phys.SetBCLoad((1 - N).astype(np.uint8), RHS)
+    phys.SolveState(x, 1e-9, 1.0, 3.0)
+    assert np.abs(phys.GetStateField() - U).max() <= 1e-7 * np.abs(U).max()
+    phys.close(); ctx.close()

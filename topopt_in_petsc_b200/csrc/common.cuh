@@ -1,0 +1,180 @@
+// common.cuh -- shared internals of libtopopt_b200.so (sm_100a only, no CPU fallback).
+//
+// Data layout in HBM:
+//   nodal dof vector  : [z_local][c][y][x]  doubles, x pitch px (multiple of 4), z-slab
+//                       stored planes [gn0,gn1) = owned planes plus one ghost plane per
+//                       neighbour; one z-plane (all three components) is contiguous so a
+//                       halo plane is one contiguous message.
+//   element field     : [z_local][y][x] doubles, pitch pe, stored layers [ge0,ge1).
+//   Dirichlet mask    : [z_local][y][x] bytes (bit c = dof c clamped), pitch px.
+// Padding columns are kept at zero in every vector so flat axpy/dot kernels can run over the
+// contiguous owned range without index arithmetic.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+#include "../../include/topopt_b200.h"
+
+namespace tob {
+
+extern thread_local std::string g_last_error;
+int set_error(const char* file, int line, const std::string& msg);
+
+#define TOB_FAIL(msg) return ::tob::set_error(__FILE__, __LINE__, (msg))
+#define TOB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return ::tob::set_error(__FILE__, __LINE__, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+#define TOB_NCCL(call)                                                                         \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess)                                                                \
+            return ::tob::set_error(__FILE__, __LINE__, std::string(#call) + ": " + ncclGetErrorString(r__)); \
+    } while (0)
+#define TOB_CHECK(call)                 \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != 0) return rc__;     \
+    } while (0)
+#define TOB_KERNEL_CHECK() TOB_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------
+// One multigrid level of this rank's z-slab (level 0 = the design/FE grid).
+// ---------------------------------------------------------------------------------------
+struct LevelGrid {
+    int nxn = 0, nyn = 0, nzn = 0;  // global node counts
+    int nex = 0, ney = 0, nez = 0;  // global element counts
+    int kn0 = 0, kn1 = 0;           // owned node planes   [kn0,kn1)  (global index)
+    int ke0 = 0, ke1 = 0;           // owned element layers [ke0,ke1)
+    int gn0 = 0, gn1 = 0;           // stored node planes   [gn0,gn1)
+    int ge0 = 0, ge1 = 0;           // stored element layers [ge0,ge1)
+    int px = 0, pe = 0;             // x pitches in doubles (nodal / element arrays)
+    int pm = 0;                     // x pitch in bytes of the Dirichlet mask (multiple of 16 for TMA)
+    long long mstride = 0;          // pm*nyn : one mask plane
+    long long nstride = 0;          // px*nyn      : one component of one plane
+    long long pstride = 0;          // 3*px*nyn    : one plane
+    long long estride = 0;          // pe*ney      : one element layer
+    long long nvec = 0;             // doubles in a stored nodal vector
+    long long evec = 0;             // doubles in a stored element field
+    long long own_off = 0, own_len = 0;  // contiguous owned range of a nodal vector
+    double dx = 0, dy = 0, dz = 0;
+    int nzl() const { return gn1 - gn0; }
+    int nzle() const { return ge1 - ge0; }
+    int zl_own0() const { return kn0 - gn0; }  // local index of first owned node plane
+    int zl_own1() const { return kn1 - gn0; }
+    long long owned_nodes() const { return (long long)nxn * nyn * (kn1 - kn0); }
+    long long owned_elems() const { return (long long)nex * ney * (ke1 - ke0); }
+};
+
+void make_level_grid(LevelGrid& g, int nxn, int nyn, int nzn, double dx, double dy, double dz, int rank, int nranks,
+                     int kn0, int kn1);
+
+// device buffer that grows on demand (staging for host pointers, scratch)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n);
+    void release();
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct tob_ctx_impl {
+    tob_grid_desc desc{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    ncclComm_t comm = nullptr;
+    LevelGrid g0;  // finest level
+    int num_sms = 148;
+    // reductions
+    double* d_partials = nullptr;  // per-CTA partial sums
+    int n_partials = 0;
+    double* d_scalars = nullptr;   // device scalar slots
+    double* h_scalars = nullptr;   // pinned mirror
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    long long launches = 0;
+    DevBuf stage[8];  // staging buffers for host<->device vectors
+    // TMA encode entry point
+    void* encode_tiled = nullptr;
+};
+
+constexpr int kScalarSlots = 64;
+constexpr int kMaxPartials = 1 << 20;
+
+// -- host/device pointer staging ----------------------------------------------------------
+bool is_device_ptr(const void* p);
+// returns device pointer holding n doubles of src (copying if src is a host pointer)
+int stage_in(tob_ctx_impl* c, int slot, const void* src, size_t nbytes, const void** dev);
+// returns a device pointer to write n bytes into; call stage_out_finish afterwards
+int stage_out_begin(tob_ctx_impl* c, int slot, void* dst, size_t nbytes, void** dev);
+int stage_out_finish(tob_ctx_impl* c, void* dst, void* dev, size_t nbytes);
+
+// -- layout conversion (vecops.cu) ----------------------------------------------------------
+int nat_to_stored_dof(tob_ctx_impl* c, const LevelGrid& g, const double* nat, double* stored);
+int stored_to_nat_dof(tob_ctx_impl* c, const LevelGrid& g, const double* stored, double* nat);
+int nat_to_stored_elem(tob_ctx_impl* c, const LevelGrid& g, const double* nat, double* stored);
+int stored_to_nat_elem(tob_ctx_impl* c, const LevelGrid& g, const double* stored, double* nat);
+int nat_to_stored_mask(tob_ctx_impl* c, const LevelGrid& g, const unsigned char* fixed_nat, unsigned char* stored);
+
+// -- halo exchange (comm.cu) -------------------------------------------------------------------
+// fills the ghost node planes of a stored nodal vector from the z-neighbours (NCCL send/recv)
+int halo_nodes(tob_ctx_impl* c, const LevelGrid& g, double* v);
+// fills ghost element layers of a stored element field from the z-neighbours (see comm.cu)
+int halo_elems(tob_ctx_impl* c, double* v, long long layer_stride, int own0, int own1, int recv_lo, int recv_hi,
+               int send_down, int send_up);
+int allreduce_sum(tob_ctx_impl* c, double* d_vals, int n);
+int allreduce_max(tob_ctx_impl* c, double* d_vals, int n);
+
+// -- reductions / vector kernels (vecops.cu) --------------------------------------------------
+int vec_zero(tob_ctx_impl* c, double* v, long long n);
+int vec_copy(tob_ctx_impl* c, double* dst, const double* src, long long n);
+// dots over the contiguous owned range; result left in d_scalars[slot] (all-reduced across ranks)
+int vec_dot(tob_ctx_impl* c, const LevelGrid& g, const double* a, const double* b, int slot);
+int read_scalars(tob_ctx_impl* c, int slot0, int n, double* out);  // syncs the stream
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; result valid in thread 0. `red` must hold >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    __syncthreads();
+    return v;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+    v = warp_max(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? red[threadIdx.x] : -1.0e300;
+    if (w == 0) v = warp_max(v);
+    __syncthreads();
+    return v;
+}
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace tob

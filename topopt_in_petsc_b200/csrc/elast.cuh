@@ -1,0 +1,46 @@
+// elast.cuh -- internal state of the LinearElasticity replacement
+#pragma once
+#include "common.cuh"
+#include "hex8.cuh"
+
+namespace tob {
+
+struct GmgHierarchy;  // gmg.cu
+
+struct tob_elast_impl {
+    tob_ctx_impl* c = nullptr;
+    const LevelGrid* g = nullptr;
+    tob_solver_opts opts{};
+    double nu = 0.3;
+    Hex8Operator op;
+    // stored-layout nodal vectors
+    double *U = nullptr, *B = nullptr, *RHS = nullptr, *R = nullptr, *P = nullptr, *Q = nullptr, *Z = nullptr;
+    double *DINV = nullptr, *NFREE = nullptr;
+    unsigned char* mask = nullptr;
+    // stored element fields
+    double *xphys_st = nullptr, *E_st = nullptr;
+    // natural-order scratch (device)
+    double *nat_dof = nullptr, *nat_dof2 = nullptr, *nat_el = nullptr, *nat_el2 = nullptr;
+    double Emin = 1e-9, Emax = 1.0, penal = 3.0;
+    double bnorm = 0.0;
+    bool have_density = false;
+    tob_solve_stats stats{};
+    GmgHierarchy* mg = nullptr;
+};
+
+int elast_create(tob_ctx_impl* c, double nu, const tob_solver_opts* opts, tob_elast_impl** out);
+void elast_destroy(tob_elast_impl* h);
+int elast_set_bc_load(tob_elast_impl* h, const unsigned char* fixed, const double* rhs);
+int elast_set_density(tob_elast_impl* h, const double* xphys_nat_dev, double Emin, double Emax, double penal);
+int elast_apply(tob_elast_impl* h, const double* u, double* y, int epi, bool mask_in, int kernel, const double* a0,
+                int* nparts);
+int elast_pcg(tob_elast_impl* h);
+int mask_to_free(tob_ctx_impl* c, const LevelGrid& g, const unsigned char* mask, double* nf);
+
+// geometric multigrid preconditioner (gmg.cu)
+int gmg_setup(tob_elast_impl* h);
+int gmg_update(tob_elast_impl* h);   // refresh coarse operators after a density change
+int gmg_vcycle(tob_elast_impl* h, const double* r, double* z);
+void gmg_destroy(tob_elast_impl* h);
+
+}  // namespace tob

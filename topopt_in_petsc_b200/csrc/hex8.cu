@@ -1,0 +1,675 @@
+// hex8.cu -- matrix-free hex8 stiffness operator for sm_100a.
+//
+// Hot kernel: k_hex8_zmarch.  One CTA owns an (x,y) tile of node columns and marches along z.
+// Every z-step a TMA bulk-tensor load (cp.async.bulk.tensor, mbarrier complete_tx) brings the next
+// nodal plane tile (3 components), the element-modulus tile of the layer below it and the
+// Dirichlet-mask tile into a 4-stage shared-memory ring.  Each thread owns one element column:
+// it forms the Walsh-Hadamard "face modes" of the new plane, combines them with the face modes
+// of the previous plane kept in registers, applies the 8 3x3 blocks of the block-diagonalised
+// element matrix scaled by the SIMP modulus, and transforms back stage by stage; partial results
+// are shared between the elements around a face / edge / node (registers along z, one shared-
+// memory exchange along y, one warp shuffle along x), so each nodal value is loaded once and
+// written once and the FP64 work is ~180 DP ops per element instead of 576 FMA.
+//
+// The dense cross-check kernel k_hex8_naive applies the 24x24 KE rows per node directly.
+#include "hex8.cuh"
+#include "vecops.cuh"
+
+namespace tob {
+
+// ---------------------------------------------------------------------------------------
+// host: element matrix and its symmetry-adapted block form
+// ---------------------------------------------------------------------------------------
+static const int kSgn[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                               {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};  // LinearElasticity.cc:118-120 node order
+// binary node index q = a + 2b + 4g  ->  reference local node
+static const int kBin2Ref[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+
+void hex8_element_matrix(double dx, double dy, double dz, double nu, double* ke) {
+    // 2x2x2 Gauss quadrature of B^T C B on the box element (LinearElasticity.cc:841-998; E = 1).
+    // For an axis-aligned box the Jacobian is diag(dx,dy,dz)/2, so physical shape-function
+    // gradients are the parent gradients scaled by 2/d.
+    const double lam = nu / ((1.0 + nu) * (1.0 - 2.0 * nu));  // :887
+    const double mu = 1.0 / (2.0 * (1.0 + nu));               // :888
+    const double gp = 0.577350269189626;                      // :898
+    const double detJ = dx * dy * dz / 8.0;
+    for (int i = 0; i < 576; i++) ke[i] = 0.0;
+    for (int a = 0; a < 8; a++) {
+        const double xi = (a & 1) ? gp : -gp, eta = (a & 2) ? gp : -gp, zeta = (a & 4) ? gp : -gp;
+        double G[8][3];  // physical gradient of N_n
+        for (int n = 0; n < 8; n++) {
+            const double sx = kSgn[n][0], sy = kSgn[n][1], sz = kSgn[n][2];
+            G[n][0] = 0.125 * sx * (1 + sy * eta) * (1 + sz * zeta) * (2.0 / dx);
+            G[n][1] = 0.125 * sy * (1 + sx * xi) * (1 + sz * zeta) * (2.0 / dy);
+            G[n][2] = 0.125 * sz * (1 + sx * xi) * (1 + sy * eta) * (2.0 / dz);
+        }
+        // ke[(n,c),(m,d)] += detJ * [ lam G_nc G_md + mu G_nd G_mc + mu delta_cd (G_n . G_m) ]
+        for (int n = 0; n < 8; n++)
+            for (int m = 0; m < 8; m++) {
+                const double gg = G[n][0] * G[m][0] + G[n][1] * G[m][1] + G[n][2] * G[m][2];
+                for (int cc = 0; cc < 3; cc++)
+                    for (int d = 0; d < 3; d++) {
+                        double v = lam * G[n][cc] * G[m][d] + mu * G[n][d] * G[m][cc];
+                        if (cc == d) v += mu * gg;
+                        ke[(3 * n + cc) * 24 + 3 * m + d] += detJ * v;
+                    }
+            }
+    }
+}
+
+int hex8_build_operator(double dx, double dy, double dz, double nu, Hex8Operator& op) {
+    hex8_element_matrix(dx, dy, dz, nu, op.KE);
+    // D = T KEbin T^T / 64
+    static double Kb[24][24], TK[24][24], D[24][24];
+    for (int q = 0; q < 8; q++)
+        for (int c = 0; c < 3; c++)
+            for (int q2 = 0; q2 < 8; q2++)
+                for (int c2 = 0; c2 < 3; c2++)
+                    Kb[3 * q + c][3 * q2 + c2] = op.KE[(3 * kBin2Ref[q] + c) * 24 + 3 * kBin2Ref[q2] + c2];
+    auto W = [](int m, int q) { return (__builtin_popcount(m & q) & 1) ? -1.0 : 1.0; };
+    for (int m = 0; m < 8; m++)
+        for (int c = 0; c < 3; c++)
+            for (int col = 0; col < 24; col++) {
+                double s = 0;
+                for (int q = 0; q < 8; q++) s += W(m, q) * Kb[3 * q + c][col];
+                TK[3 * m + c][col] = s;
+            }
+    for (int row = 0; row < 24; row++)
+        for (int m = 0; m < 8; m++)
+            for (int c = 0; c < 3; c++) {
+                double s = 0;
+                for (int q = 0; q < 8; q++) s += TK[row][3 * q + c] * W(m, q);
+                D[row][3 * m + c] = s / 64.0;
+            }
+    double dmax = 0, off = 0;
+    for (int m = 0; m < 8; m++)
+        for (int c = 0; c < 3; c++)
+            for (int m2 = 0; m2 < 8; m2++)
+                for (int c2 = 0; c2 < 3; c2++) {
+                    const double v = fabs(D[3 * m + c][3 * m2 + c2]);
+                    dmax = fmax(dmax, v);
+                    if ((m ^ (1 << c)) != (m2 ^ (1 << c2))) off = fmax(off, v);
+                }
+    op.offblock_max = off;
+    if (off > 1e-12 * dmax) TOB_FAIL("element matrix is not block-diagonal in the reflection-symmetry basis");
+    for (int rho = 0; rho < 8; rho++)
+        for (int c = 0; c < 3; c++)
+            for (int c2 = 0; c2 < 3; c2++)
+                op.blocks.b[rho][3 * c + c2] = D[3 * (rho ^ (1 << c)) + c][3 * (rho ^ (1 << c2)) + c2];
+    // rigid translations (mode 0, component c) lie in block rho = 1<<c: that row/column must vanish
+    for (int c = 0; c < 3; c++)
+        for (int c2 = 0; c2 < 3; c2++) {
+            if (fabs(op.blocks.b[1 << c][3 * c + c2]) > 1e-12 * dmax || fabs(op.blocks.b[1 << c][3 * c2 + c]) > 1e-12 * dmax)
+                TOB_FAIL("translation mode is not in the null space of KE");
+            op.blocks.b[1 << c][3 * c + c2] = 0.0;
+            op.blocks.b[1 << c][3 * c2 + c] = 0.0;
+        }
+    for (int c = 0; c < 3; c++) op.kdiag[c] = op.KE[c * 24 + c];
+    for (int n = 1; n < 8; n++)
+        for (int c = 0; c < 3; c++)
+            if (fabs(op.KE[(3 * n + c) * 24 + 3 * n + c] - op.kdiag[c]) > 1e-12 * dmax) TOB_FAIL("KE diagonal not node-invariant");
+    TOB_CUDA(cudaMalloc(&op.d_KE, sizeof(double) * 576));
+    TOB_CUDA(cudaMemcpy(op.d_KE, op.KE, sizeof(double) * 576, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void hex8_free_operator(Hex8Operator& op) {
+    if (op.d_KE) cudaFree(op.d_KE);
+    op.d_KE = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------
+// naive dense cross-check kernel: one thread per owned node, 8 x (3 x 24) KE rows
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_hex8_naive(const double* __restrict__ u, double* __restrict__ y, const double* __restrict__ E,
+             const unsigned char* __restrict__ mask, const double* __restrict__ KE, int nxn, int nyn, int nzl, int px,
+             int pe, int pm, long long nstride, long long pstride, long long estride, long long mstride, int z0, int z1,
+             int mask_in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int z = z0 + blockIdx.z;
+    if (i >= nxn || z >= z1) return;
+    const int nex = nxn - 1, ney = nyn - 1, nzle = nzl - 1;
+    double acc[3] = {0, 0, 0};
+    for (int dk = -1; dk <= 0; dk++)
+        for (int dj = -1; dj <= 0; dj++)
+            for (int di = -1; di <= 0; di++) {
+                const int ei = i + di, ej = j + dj, ek = z + dk;
+                if (ei < 0 || ei >= nex || ej < 0 || ej >= ney || ek < 0 || ek >= nzle) continue;
+                const double Ee = E[ek * estride + (long long)ej * pe + ei];
+                const int q = (-di) + 2 * (-dj) + 4 * (-dk);
+                const int rloc = (q == 2) ? 3 : (q == 3) ? 2 : (q == 6) ? 7 : (q == 7) ? 6 : q;
+                double s[3] = {0, 0, 0};
+                for (int n = 0; n < 8; n++) {
+                    const int a = (n == 1 || n == 2 || n == 5 || n == 6), b = (n == 2 || n == 3 || n == 6 || n == 7), g = n >> 2;
+                    const int ni = ei + a, nj = ej + b, nk = ek + g;
+                    const unsigned char m = mask_in ? mask[nk * mstride + (long long)nj * pm + ni] : 0;
+                    for (int c2 = 0; c2 < 3; c2++) {
+                        double uv = u[nk * pstride + c2 * nstride + (long long)nj * px + ni];
+                        if (m & (1 << c2)) uv = 0.0;
+                        for (int c = 0; c < 3; c++) s[c] = fma(__ldg(&KE[(3 * rloc + c) * 24 + 3 * n + c2]), uv, s[c]);
+                    }
+                }
+                for (int c = 0; c < 3; c++) acc[c] = fma(Ee, s[c], acc[c]);
+            }
+    const unsigned char m = mask[z * mstride + (long long)j * pm + i];
+    for (int c = 0; c < 3; c++) {
+        const long long idx = z * pstride + c * nstride + (long long)j * px + i;
+        y[idx] = (m & (1 << c)) ? u[idx] : acc[c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA / mbarrier primitives (sm_90+; SASS: UTMALDG / SYNCS)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// z-march kernel
+// ---------------------------------------------------------------------------------------
+constexpr int ZM_STAGES = 4;
+
+struct ZmParams {
+    int nxn, nyn;
+    int px;
+    long long nstride, pstride;
+    int zout0, zout1;  // local node planes written: [zout0, zout1)
+    int zchunk;        // planes per CTA along z
+    double* y;
+    const double* a0;
+    const double* a1;
+    double* o1;
+    double s0, s1;
+    double* partials;
+};
+
+template <int TY>
+struct ZmSmem {
+    static constexpr int NT = 32 * TY;
+    static constexpr int U_BYTES = 3 * NT * 8;
+    static constexpr int E_BYTES = NT * 8;
+    static constexpr int M_BYTES = NT;
+    static constexpr int STAGE_BYTES = U_BYTES + E_BYTES + M_BYTES;
+    static constexpr int XCH_BYTES = 2 * 6 * NT * 8;
+    static constexpr int BAR_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES;
+    static constexpr int TOTAL = BAR_OFF + ZM_STAGES * 8 + 128;
+};
+
+template <int TY, int EPI, bool MASK_IN>
+__global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
+k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
+              const __grid_constant__ CUtensorMap tmM, const __grid_constant__ Hex8Blocks KB,
+              const __grid_constant__ ZmParams P) {
+    using L = ZmSmem<TY>;
+    constexpr int NT = L::NT;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double red[32];
+    double* xch = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int i0 = blockIdx.x * 30 - 1, j0 = blockIdx.y * (TY - 2) - 1;
+    const int i = i0 + tx, j = j0 + ty;
+    const int z0 = P.zout0 + blockIdx.z * P.zchunk;
+    const int z1 = min(z0 + P.zchunk, P.zout1);
+    const bool compute = (tx < 31) && (ty < TY - 1);
+    const bool outthr = (tx >= 1) && (tx <= 30) && (ty >= 1) && (ty <= TY - 2) && (i < P.nxn) && (j < P.nyn);
+    const int pfirst = z0 - 1;        // first node plane consumed (prologue)
+    const int nplanes = z1 - z0 + 2;  // planes pfirst .. z1
+    double part = 0.0;
+
+    if (z0 < z1) {
+        if (tid == 0) {
+            for (int s = 0; s < ZM_STAGES; s++) mbar_init(&bars[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+
+        auto issue = [&](int pidx) {  // pidx = plane counter 0..nplanes-1, plane = pfirst + pidx
+            const int s = pidx % ZM_STAGES;
+            unsigned char* st = smem_raw + s * L::STAGE_BYTES;
+            const int p = pfirst + pidx;
+            mbar_expect_tx(&bars[s], L::STAGE_BYTES);
+            tma_load_4d(st, &tmU, &bars[s], i0, j0, 0, p);
+            tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0, j0, p - 1);
+            tma_load_3d(st + L::U_BYTES + L::E_BYTES, &tmM, &bars[s], i0, j0, p);
+        };
+        if (tid == 0)
+            for (int s = 0; s < ZM_STAGES && s < nplanes; s++) issue(s);
+
+        double fprev[3][4];  // face modes of the lower plane of the current element
+        double upacc[3][4];  // upper-face contributions of the previous element
+        double uown[3];      // own node value on the plane being completed
+        unsigned mown = 0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            uown[c] = 0.0;
+#pragma unroll
+            for (int f = 0; f < 4; f++) { fprev[c][f] = 0.0; upacc[c][f] = 0.0; }
+        }
+        const int o = ty * 32 + tx;
+
+        // face modes of one plane tile: X stage on rows j and j+1, then Y stage
+        auto face_modes = [&](const unsigned char* st, double (&fm)[3][4]) {
+            const double* su = reinterpret_cast<const double*>(st);
+            unsigned m00 = 0, m10 = 0, m01 = 0, m11 = 0;
+            if (MASK_IN) {
+                const unsigned char* sm = st + L::U_BYTES + L::E_BYTES;
+                m00 = sm[o]; m10 = sm[o + 1]; m01 = sm[o + 32]; m11 = sm[o + 33];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double a = su[c * NT + o], b = su[c * NT + o + 1], cc = su[c * NT + o + 32], d = su[c * NT + o + 33];
+                if (MASK_IN) {
+                    if (m00 & (1u << c)) a = 0.0;
+                    if (m10 & (1u << c)) b = 0.0;
+                    if (m01 & (1u << c)) cc = 0.0;
+                    if (m11 & (1u << c)) d = 0.0;
+                }
+                const double s0 = a + b, d0 = a - b, s1 = cc + d, d1 = cc - d;
+                fm[c][0] = s0 + s1;
+                fm[c][1] = d0 + d1;
+                fm[c][2] = s0 - s1;
+                fm[c][3] = d0 - d1;
+            }
+        };
+
+        // ---- prologue: plane pfirst ------------------------------------------------------
+        {
+            mbar_wait(&bars[0], 0);
+            const unsigned char* st = smem_raw;
+            const double* su = reinterpret_cast<const double*>(st);
+#pragma unroll
+            for (int c = 0; c < 3; c++) uown[c] = su[c * NT + o];
+            mown = (st + L::U_BYTES + L::E_BYTES)[o];
+            if (compute) face_modes(st, fprev);
+            __syncthreads();
+            if (tid == 0 && ZM_STAGES < nplanes) issue(ZM_STAGES);
+        }
+
+        // ---- march: step t handles element layer e = pfirst + t, upper plane pfirst + t + 1 -----
+        const int nsteps = z1 - pfirst;
+        for (int t = 0; t < nsteps; t++) {
+            const int pidx = t + 1;
+            const int s = pidx % ZM_STAGES;
+            const unsigned char* st = smem_raw + s * L::STAGE_BYTES;
+            mbar_wait(&bars[s], (pidx / ZM_STAGES) & 1);
+            const double* su = reinterpret_cast<const double*>(st);
+            double unew[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) unew[c] = su[c * NT + o];
+            const unsigned mnew = (st + L::U_BYTES + L::E_BYTES)[o];
+
+            double ex0[3][2];  // edge (row j) contributions of my face
+            double* xw = xch + (t & 1) * 6 * NT;
+            if (compute) {
+                double fnew[3][4];
+                face_modes(st, fnew);
+                const double Ee = reinterpret_cast<const double*>(st + L::U_BYTES)[o];
+                // Z stage: element modes  uh[c][ma + 2 mb + 4 mg]
+                double uh[3][8];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int f = 0; f < 4; f++) {
+                        uh[c][f] = fprev[c][f] + fnew[c][f];
+                        uh[c][4 + f] = fprev[c][f] - fnew[c][f];
+                        fprev[c][f] = fnew[c][f];
+                    }
+                // 8 blocks of 3x3, scaled by the modulus
+                double yh[3][8];
+#pragma unroll
+                for (int rho = 0; rho < 8; rho++) {
+                    const double in0 = uh[0][rho ^ 1], in1 = uh[1][rho ^ 2], in2 = uh[2][rho ^ 4];
+                    double o0, o1, o2;
+                    if (rho == 1) {
+                        o0 = 0.0;
+                        o1 = KB.b[1][4] * in1 + KB.b[1][5] * in2;
+                        o2 = KB.b[1][7] * in1 + KB.b[1][8] * in2;
+                    } else if (rho == 2) {
+                        o1 = 0.0;
+                        o0 = KB.b[2][0] * in0 + KB.b[2][2] * in2;
+                        o2 = KB.b[2][6] * in0 + KB.b[2][8] * in2;
+                    } else if (rho == 4) {
+                        o2 = 0.0;
+                        o0 = KB.b[4][0] * in0 + KB.b[4][1] * in1;
+                        o1 = KB.b[4][3] * in0 + KB.b[4][4] * in1;
+                    } else {
+                        o0 = KB.b[rho][0] * in0 + KB.b[rho][1] * in1 + KB.b[rho][2] * in2;
+                        o1 = KB.b[rho][3] * in0 + KB.b[rho][4] * in1 + KB.b[rho][5] * in2;
+                        o2 = KB.b[rho][6] * in0 + KB.b[rho][7] * in1 + KB.b[rho][8] * in2;
+                    }
+                    yh[0][rho ^ 1] = Ee * o0;
+                    yh[1][rho ^ 2] = Ee * o1;
+                    yh[2][rho ^ 4] = Ee * o2;
+                }
+                // Z' stage + face totals (lower face of this element + upper face of the previous one)
+                double ht[3][4];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int f = 0; f < 4; f++) {
+                        ht[c][f] = (yh[c][f] + yh[c][4 + f]) + upacc[c][f];
+                        upacc[c][f] = yh[c][f] - yh[c][4 + f];
+                    }
+                // Y' stage: row j part stays, row j+1 part goes to the thread above
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int ma = 0; ma < 2; ma++) {
+                        ex0[c][ma] = ht[c][ma] + ht[c][ma + 2];
+                        xw[(2 * c + ma) * NT + o] = ht[c][ma] - ht[c][ma + 2];
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { ex0[c][0] = 0.0; ex0[c][1] = 0.0; }
+            }
+            __syncthreads();
+            if (tid == 0 && pidx + ZM_STAGES < nplanes) issue(pidx + ZM_STAGES);
+
+            // edge totals, X' stage, node totals
+            double v[3], vr[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double e0 = ex0[c][0], e1 = ex0[c][1];
+                if (ty >= 1) {
+                    e0 += xw[(2 * c + 0) * NT + o - 32];
+                    e1 += xw[(2 * c + 1) * NT + o - 32];
+                }
+                v[c] = e0 + e1;
+                vr[c] = e0 - e1;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[c] += __shfl_up_sync(0xffffffffu, vr[c], 1);
+
+            const int e = pfirst + t;  // node plane completed by this step
+            if (outthr && e >= z0) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const long long idx = e * P.pstride + c * P.nstride + (long long)j * P.px + i;
+                    const bool fixed = (mown >> c) & 1u;
+                    const double au = fixed ? uown[c] : v[c];
+                    if (EPI == EPI_Y) {
+                        P.y[idx] = au;
+                    } else if (EPI == EPI_DOT) {
+                        P.y[idx] = au;
+                        part = fma(uown[c], au, part);
+                    } else if (EPI == EPI_RESID) {
+                        const double r = P.a0[idx] - au;
+                        P.y[idx] = r;
+                        part = fma(r, r, part);
+                    } else {  // EPI_CHEB
+                        const double r = P.a0[idx] - au;
+                        const double dn = P.s0 * P.o1[idx] + P.s1 * P.a1[idx] * r;
+                        P.o1[idx] = dn;
+                        P.y[idx] = uown[c] + dn;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) uown[c] = unew[c];
+            mown = mnew;
+        }
+    }
+    if (EPI == EPI_DOT || EPI == EPI_RESID) {
+        part = block_sum(part, red);
+        if (tid == 0) P.partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = part;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launch
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_map(tob_ctx_impl* c, CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base,
+                      const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(c->encode_tiled)(
+        tm, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) TOB_FAIL("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
+template <int TY, int EPI, bool MASK_IN>
+static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
+    using L = ZmSmem<TY>;
+    CUtensorMap tmU, tmE, tmM;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, 3, (cuuint64_t)g.nzl()};
+        cuuint64_t str[3] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.nstride * 8, (cuuint64_t)g.pstride * 8};
+        cuuint32_t box[4] = {32, (cuuint32_t)TY, 3, 1};
+        TOB_CHECK(encode_map(c, &tmU, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, a.u, dims, str, box));
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g.nex, (cuuint64_t)g.ney, (cuuint64_t)g.nzle()};
+        cuuint64_t str[2] = {(cuuint64_t)g.pe * 8, (cuuint64_t)g.estride * 8};
+        cuuint32_t box[3] = {32, (cuuint32_t)TY, 1};
+        TOB_CHECK(encode_map(c, &tmE, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, a.E, dims, str, box));
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, (cuuint64_t)g.nzl()};
+        cuuint64_t str[2] = {(cuuint64_t)g.pm, (cuuint64_t)g.mstride};
+        cuuint32_t box[3] = {32, (cuuint32_t)TY, 1};
+        TOB_CHECK(encode_map(c, &tmM, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, a.mask, dims, str, box));
+    }
+    ZmParams P;
+    P.nxn = g.nxn; P.nyn = g.nyn; P.px = g.px; P.nstride = g.nstride; P.pstride = g.pstride;
+    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1();
+    P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
+    const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, TY - 2);
+    const int nz = P.zout1 - P.zout0;
+    // z-chunks: enough CTAs for >= ~3 waves, but chunks of at least 8 planes (each chunk recomputes one layer)
+    const int ctas_per_wave = c->num_sms * ((TY <= 8) ? 2 : 1);
+    int nch = div_up(3LL * ctas_per_wave, (long long)gx * gy);
+    int max_ch = nz / 8 > 0 ? nz / 8 : 1;
+    if (nch > max_ch) nch = max_ch;
+    if (nch < 1) nch = 1;
+    P.zchunk = div_up(nz, nch);
+    nch = div_up(nz, P.zchunk);
+    if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
+    auto kern = k_hex8_zmarch<TY, EPI, MASK_IN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, tmM, op.blocks, P);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    if (nparts) *nparts = (EPI == EPI_DOT || EPI == EPI_RESID) ? gx * gy * nch : 0;
+    return 0;
+}
+
+template <int TY>
+static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
+    if (a.mask_in) {
+        switch (a.epi) {
+            case EPI_Y: return launch_zm<TY, EPI_Y, true>(c, g, op, a, nparts);
+            case EPI_DOT: return launch_zm<TY, EPI_DOT, true>(c, g, op, a, nparts);
+            case EPI_RESID: return launch_zm<TY, EPI_RESID, true>(c, g, op, a, nparts);
+            default: return launch_zm<TY, EPI_CHEB, true>(c, g, op, a, nparts);
+        }
+    }
+    switch (a.epi) {
+        case EPI_Y: return launch_zm<TY, EPI_Y, false>(c, g, op, a, nparts);
+        case EPI_DOT: return launch_zm<TY, EPI_DOT, false>(c, g, op, a, nparts);
+        case EPI_RESID: return launch_zm<TY, EPI_RESID, false>(c, g, op, a, nparts);
+        default: return launch_zm<TY, EPI_CHEB, false>(c, g, op, a, nparts);
+    }
+}
+
+int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
+    if (nparts) *nparts = 0;
+    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM8 : a.kernel;
+    if (kernel == SPMV_NAIVE) {
+        if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");
+        dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());
+        k_hex8_naive<<<grid, 128, 0, c->stream>>>(a.u, a.y, a.E, a.mask, op.d_KE, g.nxn, g.nyn, g.nzl(), g.px, g.pe, g.pm,
+                                                  g.nstride, g.pstride, g.estride, g.mstride, g.zl_own0(), g.zl_own1(),
+                                                  a.mask_in ? 1 : 0);
+        c->launches++;
+        TOB_KERNEL_CHECK();
+        return 0;
+    }
+    if (kernel == SPMV_ZM16) return dispatch_zm<16>(c, g, op, a, nparts);
+    return dispatch_zm<8>(c, g, op, a, nparts);
+}
+
+// ---------------------------------------------------------------------------------------
+// diagonal, SIMP modulus, compliance / sensitivities
+// ---------------------------------------------------------------------------------------
+__global__ void k_hex8_diag(const double* __restrict__ E, const unsigned char* __restrict__ mask, double* __restrict__ d,
+                            double kd0, double kd1, double kd2, int nxn, int nyn, int nzl, int px, int pe, int pm,
+                            long long nstride, long long pstride, long long estride, long long mstride, int z0, int z1,
+                            int invert) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int z = z0 + blockIdx.z;
+    if (i >= nxn || z >= z1) return;
+    const int nex = nxn - 1, ney = nyn - 1, nzle = nzl - 1;
+    double s = 0.0;
+    for (int dk = -1; dk <= 0; dk++)
+        for (int dj = -1; dj <= 0; dj++)
+            for (int di = -1; di <= 0; di++) {
+                const int ei = i + di, ej = j + dj, ek = z + dk;
+                if (ei < 0 || ei >= nex || ej < 0 || ej >= ney || ek < 0 || ek >= nzle) continue;
+                s += E[ek * estride + (long long)ej * pe + ei];
+            }
+    const unsigned char m = mask[z * mstride + (long long)j * pm + i];
+    const double kd[3] = {kd0, kd1, kd2};
+    for (int c = 0; c < 3; c++) {
+        double v = (m & (1 << c)) ? 1.0 : kd[c] * s;
+        d[z * pstride + c * nstride + (long long)j * px + i] = invert ? 1.0 / v : v;
+    }
+}
+
+int hex8_diag_inv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const double* E,
+                  const unsigned char* mask, double* d, bool invert) {
+    dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());
+    k_hex8_diag<<<grid, 128, 0, c->stream>>>(E, mask, d, op.kdiag[0], op.kdiag[1], op.kdiag[2], g.nxn, g.nyn, g.nzl(), g.px,
+                                             g.pe, g.pm, g.nstride, g.pstride, g.estride, g.mstride, g.zl_own0(),
+                                             g.zl_own1(), invert ? 1 : 0);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(kFlatThreads) k_simp(const double* __restrict__ x, double* __restrict__ E, long long n,
+                                                       double Emin, double Emax, double penal) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        E[i] = Emin + pow(x[i], penal) * (Emax - Emin);
+}
+int simp_modulus(tob_ctx_impl* c, const double* x, double* E, long long n, double Emin, double Emax, double penal) {
+    k_simp<<<flat_grid(c, n), kFlatThreads, 0, c->stream>>>(x, E, n, Emin, Emax, penal);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+// one thread per owned element: uKu = uh^T D uh in the symmetry basis
+__global__ void __launch_bounds__(128)
+k_hex8_compliance(const double* __restrict__ u, const double* __restrict__ xphys, const double* __restrict__ E,
+                  double* __restrict__ dfdx, const __grid_constant__ Hex8Blocks KB, int nex, int ney, int px, int pe,
+                  long long nstride, long long pstride, long long estride, int l0, int l1, double penal, double dE,
+                  double* __restrict__ partials) {
+    __shared__ double red[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    const int l = l0 + blockIdx.z;  // local element layer
+    double pf = 0.0, px_sum = 0.0;
+    if (i < nex && l < l1) {
+        double uh[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double w[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                w[q] = u[(l + (q >> 2)) * pstride + c * nstride + (long long)(j + ((q >> 1) & 1)) * px + i + (q & 1)];
+#pragma unroll
+            for (int h = 1; h < 8; h <<= 1)
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (!(q & h)) { const double a = w[q], b = w[q | h]; w[q] = a + b; w[q | h] = a - b; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) uh[c][q] = w[q];
+        }
+        double uKu = 0.0;
+#pragma unroll
+        for (int rho = 0; rho < 8; rho++) {
+            const double in[3] = {uh[0][rho ^ 1], uh[1][rho ^ 2], uh[2][rho ^ 4]};
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; c2++) uKu = fma(in[c] * KB.b[rho][3 * c + c2], in[c2], uKu);
+        }
+        const long long eidx = l * estride + (long long)j * pe + i;
+        const double xp = xphys[eidx];
+        pf = E[eidx] * uKu;
+        px_sum = xp;
+        dfdx[(long long)i + (long long)nex * (j + (long long)ney * (l - l0))] = -penal * pow(xp, penal - 1.0) * dE * uKu;
+    }
+    pf = block_sum(pf, red);
+    px_sum = block_sum(px_sum, red);
+    if (threadIdx.x == 0) {
+        const long long nb = (long long)gridDim.x * gridDim.y * gridDim.z;
+        const long long b = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partials[b] = pf;
+        partials[nb + b] = px_sum;
+    }
+}
+
+int hex8_compliance(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const double* u, const double* xphys,
+                    const double* E, double penal, double Emin, double Emax, double* dfdx_nat, int slot) {
+    const int l0 = g.ke0 - g.ge0, l1 = g.ke1 - g.ge0;
+    dim3 grid(div_up(g.nex, 128), g.ney, l1 - l0);
+    const long long nb = (long long)grid.x * grid.y * grid.z;
+    if (2 * nb > kMaxPartials) {
+        // large grids: fall back to chunks along z so the partial buffer suffices
+        TOB_FAIL("compliance partial buffer too small");
+    }
+    k_hex8_compliance<<<grid, 128, 0, c->stream>>>(u, xphys, E, dfdx_nat, op.blocks, g.nex, g.ney, g.px, g.pe, g.nstride,
+                                                   g.pstride, g.estride, l0, l1, penal, Emax - Emin, c->d_partials);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return finalize_sum(c, (int)nb, 2, slot, true);
+}
+
+}  // namespace tob

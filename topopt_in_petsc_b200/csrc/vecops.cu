@@ -1,0 +1,294 @@
+// vecops.cu -- layout conversion at the C-ABI boundary, flat vector kernels and deterministic
+// two-stage reductions.  The reference does these through PETSc Vec ops (VecAXPY, VecDot,
+// VecPointwiseMult ...) inside KSPSolve (LinearElasticity.cc:204); here they are fused streaming
+// kernels over the contiguous owned range of the stored layout.
+#include "common.cuh"
+#include "vecops.cuh"
+
+namespace tob {
+
+// ---------------------------------------------------------------------------------------
+// natural <-> stored layout
+// ---------------------------------------------------------------------------------------
+__global__ void k_nat_to_stored_dof(const double* __restrict__ nat, double* __restrict__ st, int nxn, int nyn, int nzo,
+                                    int px, long long nstride, long long pstride, int zl0) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)nxn * nyn * nzo * 3;
+    if (idx >= tot) return;
+    int i = idx % nxn; long long t = idx / nxn;
+    int j = t % nyn; t /= nyn;
+    int c = t % 3; int k = t / 3;
+    st[(k + zl0) * pstride + c * nstride + (long long)j * px + i] = nat[3 * ((long long)i + (long long)nxn * (j + (long long)nyn * k)) + c];
+}
+__global__ void k_stored_to_nat_dof(const double* __restrict__ st, double* __restrict__ nat, int nxn, int nyn, int nzo,
+                                    int px, long long nstride, long long pstride, int zl0) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)nxn * nyn * nzo * 3;
+    if (idx >= tot) return;
+    int i = idx % nxn; long long t = idx / nxn;
+    int j = t % nyn; t /= nyn;
+    int c = t % 3; int k = t / 3;
+    nat[3 * ((long long)i + (long long)nxn * (j + (long long)nyn * k)) + c] = st[(k + zl0) * pstride + c * nstride + (long long)j * px + i];
+}
+__global__ void k_nat_to_stored_elem(const double* __restrict__ nat, double* __restrict__ st, int nex, int ney, int nzo,
+                                     int pe, long long estride, int zl0) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)nex * ney * nzo;
+    if (idx >= tot) return;
+    int i = idx % nex; long long t = idx / nex;
+    int j = t % ney; int k = t / ney;
+    st[(k + zl0) * estride + (long long)j * pe + i] = nat[idx];
+}
+__global__ void k_stored_to_nat_elem(const double* __restrict__ st, double* __restrict__ nat, int nex, int ney, int nzo,
+                                     int pe, long long estride, int zl0) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)nex * ney * nzo;
+    if (idx >= tot) return;
+    int i = idx % nex; long long t = idx / nex;
+    int j = t % ney; int k = t / ney;
+    nat[idx] = st[(k + zl0) * estride + (long long)j * pe + i];
+}
+__global__ void k_nat_to_stored_mask(const unsigned char* __restrict__ fixed, unsigned char* __restrict__ st, int nxn,
+                                     int nyn, int nzo, int pm, int zl0) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)nxn * nyn * nzo;
+    if (idx >= tot) return;
+    int i = idx % nxn; long long t = idx / nxn;
+    int j = t % nyn; int k = t / nyn;
+    unsigned char m = 0;
+    for (int c = 0; c < 3; c++) m |= (fixed[3 * idx + c] ? 1 : 0) << c;
+    st[((long long)(k + zl0) * nyn + j) * pm + i] = m;
+}
+
+#define LAUNCH1D(kern, tot, ...)                                                  \
+    do {                                                                          \
+        long long tot__ = (tot);                                                  \
+        if (tot__ > 0) {                                                          \
+            kern<<<div_up(tot__, 256), 256, 0, c->stream>>>(__VA_ARGS__);         \
+            c->launches++;                                                        \
+            TOB_KERNEL_CHECK();                                                   \
+        }                                                                         \
+    } while (0)
+
+int nat_to_stored_dof(tob_ctx_impl* c, const LevelGrid& g, const double* nat, double* st) {
+    int nzo = g.kn1 - g.kn0;
+    LAUNCH1D(k_nat_to_stored_dof, (long long)g.nxn * g.nyn * nzo * 3, nat, st, g.nxn, g.nyn, nzo, g.px, g.nstride,
+             g.pstride, g.zl_own0());
+    return 0;
+}
+int stored_to_nat_dof(tob_ctx_impl* c, const LevelGrid& g, const double* st, double* nat) {
+    int nzo = g.kn1 - g.kn0;
+    LAUNCH1D(k_stored_to_nat_dof, (long long)g.nxn * g.nyn * nzo * 3, st, nat, g.nxn, g.nyn, nzo, g.px, g.nstride,
+             g.pstride, g.zl_own0());
+    return 0;
+}
+int nat_to_stored_elem(tob_ctx_impl* c, const LevelGrid& g, const double* nat, double* st) {
+    int nzo = g.ke1 - g.ke0;
+    LAUNCH1D(k_nat_to_stored_elem, (long long)g.nex * g.ney * nzo, nat, st, g.nex, g.ney, nzo, g.pe, g.estride,
+             g.ke0 - g.ge0);
+    return 0;
+}
+int stored_to_nat_elem(tob_ctx_impl* c, const LevelGrid& g, const double* st, double* nat) {
+    int nzo = g.ke1 - g.ke0;
+    LAUNCH1D(k_stored_to_nat_elem, (long long)g.nex * g.ney * nzo, st, nat, g.nex, g.ney, nzo, g.pe, g.estride,
+             g.ke0 - g.ge0);
+    return 0;
+}
+int nat_to_stored_mask(tob_ctx_impl* c, const LevelGrid& g, const unsigned char* fixed, unsigned char* st) {
+    int nzo = g.kn1 - g.kn0;
+    LAUNCH1D(k_nat_to_stored_mask, (long long)g.nxn * g.nyn * nzo, fixed, st, g.nxn, g.nyn, nzo, g.pm, g.zl_own0());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// flat kernels
+// ---------------------------------------------------------------------------------------
+int vec_zero(tob_ctx_impl* c, double* v, long long n) {
+    TOB_CUDA(cudaMemsetAsync(v, 0, sizeof(double) * n, c->stream));
+    return 0;
+}
+int vec_copy(tob_ctx_impl* c, double* dst, const double* src, long long n) {
+    TOB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+__global__ void k_finalize_sum(const double* __restrict__ partials, int n, double* __restrict__ out, int nvals) {
+    __shared__ double red[32];
+    for (int v = 0; v < nvals; v++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[(long long)v * n + i];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) out[v] = s;
+    }
+}
+__global__ void k_finalize_max(const double* __restrict__ partials, int n, double* __restrict__ out, int nvals) {
+    __shared__ double red[32];
+    for (int v = 0; v < nvals; v++) {
+        double s = -1.0e300;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmax(s, partials[(long long)v * n + i]);
+        s = block_max(s, red);
+        if (threadIdx.x == 0) out[v] = s;
+    }
+}
+
+int finalize_sum_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce) {
+    k_finalize_sum<<<1, 256, 0, c->stream>>>(c->d_partials, nblocks, d_out, nvals);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    if (allreduce) TOB_CHECK(allreduce_sum(c, d_out, nvals));
+    return 0;
+}
+int finalize_max_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce) {
+    k_finalize_max<<<1, 256, 0, c->stream>>>(c->d_partials, nblocks, d_out, nvals);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    if (allreduce) TOB_CHECK(allreduce_max(c, d_out, nvals));
+    return 0;
+}
+int finalize_sum(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allreduce) {
+    return finalize_sum_to(c, nblocks, nvals, c->d_scalars + slot, allreduce);
+}
+int finalize_max(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allreduce) {
+    return finalize_max_to(c, nblocks, nvals, c->d_scalars + slot, allreduce);
+}
+
+int flat_grid(tob_ctx_impl* c, long long n) {
+    long long want = (n + 2 * kFlatThreads - 1) / (2 * kFlatThreads);
+    long long cap = (long long)c->num_sms * 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+__global__ void __launch_bounds__(kFlatThreads) k_dot(const double* __restrict__ a, const double* __restrict__ b,
+                                                      long long n, double* __restrict__ partials) {
+    __shared__ double red[32];
+    double s = 0.0;
+    const double2* a2 = reinterpret_cast<const double2*>(a);
+    const double2* b2 = reinterpret_cast<const double2*>(b);
+    long long n2 = n >> 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 x = a2[i], y = b2[i];
+        s = fma(x.x, y.x, s);
+        s = fma(x.y, y.y, s);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) s = fma(a[n - 1], b[n - 1], s);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+int vec_dot(tob_ctx_impl* c, const LevelGrid& g, const double* a, const double* b, int slot) {
+    int nb = flat_grid(c, g.own_len);
+    k_dot<<<nb, kFlatThreads, 0, c->stream>>>(a + g.own_off, b + g.own_off, g.own_len, c->d_partials);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return finalize_sum(c, nb, 1, slot, true);
+}
+
+// ---- PCG fused updates ------------------------------------------------------------------
+// x += alpha p ; r -= alpha q ; partial sums of r.r and (Jacobi) r.dinv.r, alpha = s[num]/s[den]
+__global__ void __launch_bounds__(kFlatThreads)
+k_pcg_update_xr(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                const double* __restrict__ q, const double* __restrict__ dinv, long long n,
+                const double* __restrict__ scal, int s_num, int s_den, double* __restrict__ partials) {
+    __shared__ double red[32];
+    const double alpha = scal[s_num] / scal[s_den];
+    double rr = 0.0, rz = 0.0;
+    long long n2 = n >> 1;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    const double2* q2 = reinterpret_cast<const double2*>(q);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 xv = x2[i], rv = r2[i], pv = p2[i], qv = q2[i];
+        xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
+        x2[i] = xv; r2[i] = rv;
+        rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
+        if (dinv) {
+            double2 dv = d2[i];
+            rz = fma(rv.x * dv.x, rv.x, rz); rz = fma(rv.y * dv.y, rv.y, rz);
+        }
+    }
+    rr = block_sum(rr, red);
+    rz = block_sum(rz, red);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = rr; partials[gridDim.x + blockIdx.x] = rz; }
+}
+
+// p = z + beta p with z = dinv.r (Jacobi) or an explicit z ; beta = s[num]/s[den]
+__global__ void __launch_bounds__(kFlatThreads)
+k_pcg_update_p(double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ dinv, long long n,
+               const double* __restrict__ scal, int s_num, int s_den, int first) {
+    const double beta = first ? 0.0 : scal[s_num] / scal[s_den];
+    long long n2 = n >> 1;
+    double2* p2 = reinterpret_cast<double2*>(p);
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 rv = r2[i], pv = p2[i];
+        if (dinv) { double2 dv = d2[i]; rv.x *= dv.x; rv.y *= dv.y; }
+        pv.x = fma(beta, pv.x, rv.x); pv.y = fma(beta, pv.y, rv.y);
+        p2[i] = pv;
+    }
+}
+
+int pcg_update_xr(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q,
+                  const double* dinv, int s_num, int s_den, int slot_rr_rz) {
+    int nb = flat_grid(c, g.own_len);
+    k_pcg_update_xr<<<nb, kFlatThreads, 0, c->stream>>>(x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off,
+                                                      dinv ? dinv + g.own_off : nullptr, g.own_len, c->d_scalars,
+                                                      s_num, s_den, c->d_partials);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return finalize_sum(c, nb, 2, slot_rr_rz, true);
+}
+int pcg_update_p(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* z_or_r, const double* dinv, int s_num,
+                 int s_den, int first) {
+    int nb = flat_grid(c, g.own_len);
+    k_pcg_update_p<<<nb, kFlatThreads, 0, c->stream>>>(p + g.own_off, z_or_r + g.own_off,
+                                                     dinv ? dinv + g.own_off : nullptr, g.own_len, c->d_scalars, s_num,
+                                                     s_den, first);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+// y = a*x + b*y  /  w = a*x + b*y  style helpers (host scalars)
+__global__ void __launch_bounds__(kFlatThreads) k_axpby(double* __restrict__ y, const double* __restrict__ x, double a,
+                                                        double b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = a * x[i] + b * y[i];
+}
+int vec_axpby(tob_ctx_impl* c, double* y, const double* x, double a, double b, long long n) {
+    if (n <= 0) return 0;
+    k_axpby<<<flat_grid(c, n), kFlatThreads, 0, c->stream>>>(y, x, a, b, n);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+__global__ void __launch_bounds__(kFlatThreads) k_pointwise_mult(double* __restrict__ y, const double* __restrict__ a,
+                                                                 const double* __restrict__ b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = a[i] * b[i];
+}
+int vec_pointwise_mult(tob_ctx_impl* c, double* y, const double* a, const double* b, long long n) {
+    if (n <= 0) return 0;
+    k_pointwise_mult<<<flat_grid(c, n), kFlatThreads, 0, c->stream>>>(y, a, b, n);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+__global__ void __launch_bounds__(kFlatThreads) k_fill(double* __restrict__ y, double v, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = v;
+}
+int vec_fill(tob_ctx_impl* c, double* y, double v, long long n) {
+    if (n <= 0) return 0;
+    k_fill<<<flat_grid(c, n), kFlatThreads, 0, c->stream>>>(y, v, n);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+}  // namespace tob

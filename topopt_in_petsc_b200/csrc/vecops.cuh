@@ -1,0 +1,18 @@
+// vecops.cuh -- declarations of the flat vector kernels / reductions in vecops.cu
+#pragma once
+#include "common.cuh"
+namespace tob {
+constexpr int kFlatThreads = 256;
+int flat_grid(tob_ctx_impl* c, long long n);
+int finalize_sum(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allreduce);
+int finalize_max(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allreduce);
+int finalize_sum_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce);
+int finalize_max_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce);
+int pcg_update_xr(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q,
+                  const double* dinv, int s_num, int s_den, int slot_rr_rz);
+int pcg_update_p(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* z_or_r, const double* dinv, int s_num,
+                 int s_den, int first);
+int vec_axpby(tob_ctx_impl* c, double* y, const double* x, double a, double b, long long n);
+int vec_pointwise_mult(tob_ctx_impl* c, double* y, const double* a, const double* b, long long n);
+int vec_fill(tob_ctx_impl* c, double* y, double v, long long n);
+}  // namespace tob
