@@ -60,6 +60,8 @@ typedef struct tob_solve_stats {
     double seconds;      /* device time of the solve (CUDA events) */
     int spmv_calls;
     int kernel_launches; /* launches of this library's kernels since the last reset */
+    double spmv_seconds; /* summed device time of the fine-level SpMV launches timed with CUDA events (profiling on) */
+    int spmv_timed;      /* number of SpMV launches in spmv_seconds */
 } tob_solve_stats;
 
 const char* tob_last_error(void);
@@ -80,6 +82,10 @@ void* tob_ctx_stream(tob_ctx* ctx);
 int tob_dev_alloc(tob_ctx* ctx, long long nbytes, void** out);
 int tob_dev_free(tob_ctx* ctx, void* p);
 int tob_memcpy(tob_ctx* ctx, void* dst, const void* src, long long nbytes); /* any direction, on the ctx stream, synchronous */
+/* 128-byte ncclUniqueId for tob_grid_desc.nccl_id (rank 0 creates it, the launcher broadcasts it; stands in for MPI_Init) */
+int tob_nccl_unique_id(void* out128);
+/* VecScale (main.cc:73) on a host or device vector of n doubles */
+int tob_vec_scale(tob_ctx* ctx, double* v, double a, long long n);
 
 /* ---- LinearElasticity ------------------------------------------------ */
 void tob_solver_opts_default(tob_solver_opts* o);
@@ -112,6 +118,8 @@ int tob_elast_set_state(tob_elast* h, const double* U);
 int tob_elast_get_rhs(tob_elast* h, double* rhs);
 int tob_elast_last_stats(tob_elast* h, tob_solve_stats* s);
 int tob_elast_set_opts(tob_elast* h, const tob_solver_opts* opts);
+/* time every fine-level SpMV launch of the next solves with CUDA event pairs (tob_solve_stats.spmv_seconds) */
+int tob_elast_set_profile(tob_elast* h, int on);
 
 /* ---- Filter / PDEFilt ------------------------------------------------ */
 /* Filter::Filter + SetUp (Filter.cc:25-38,290-463); type 0 sens, 1 dens, 2 PDE, else none; rmin physical length */

@@ -5,4 +5,4 @@ include/topopt_b200.h) plus the C++ host classes under host/.  This Python packa
 ctypes mirror used by tests and bench.py.
 """
 from ._lib import TobError, load, LIB_PATH  # noqa: F401
-from .api import Context, DevVec, Filter, LinearElasticity, MMA, solver_opts  # noqa: F401
+from .api import Context, DevVec, Filter, LinearElasticity, MMA, nccl_unique_id, solver_opts  # noqa: F401

@@ -31,7 +31,8 @@ class SolverOpts(C.Structure):
 
 class SolveStats(C.Structure):
     _fields_ = [("iterations", C.c_int), ("rel_residual", C.c_double), ("seconds", C.c_double),
-                ("spmv_calls", C.c_int), ("kernel_launches", C.c_int)]
+                ("spmv_calls", C.c_int), ("kernel_launches", C.c_int), ("spmv_seconds", C.c_double),
+                ("spmv_timed", C.c_int)]
 
 
 _lib = None
@@ -60,6 +61,9 @@ SIGNATURES = {
     "tob_dev_alloc": (_I, [_P, _LL, _PP]),
     "tob_dev_free": (_I, [_P, _P]),
     "tob_memcpy": (_I, [_P, _P, _P, _LL]),
+    "tob_nccl_unique_id": (_I, [_P]),
+    "tob_vec_scale": (_I, [_P, _P, _D, _LL]),
+    "tob_elast_set_profile": (_I, [_P, _I]),
     "tob_solver_opts_default": (None, [C.POINTER(SolverOpts)]),
     "tob_elast_create": (_I, [_P, _D, C.POINTER(SolverOpts), _PP]),
     "tob_elast_destroy": (_I, [_P]),

@@ -47,6 +47,12 @@ class DevVec:
             self.ptr = None
 
 
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(_lib.load().tob_nccl_unique_id(buf))
+    return buf.raw
+
+
 def _ptr(v):
     if v is None:
         return None
@@ -102,6 +108,11 @@ class Context:
         if self.h:
             self.lib.tob_ctx_destroy(self.h)
             self.h = None
+
+    def scale(self, v, a, n=None):
+        """VecScale (main.cc:73) on a host ndarray or DevVec."""
+        n = int(n if n is not None else (v.n if isinstance(v, DevVec) else v.size))
+        check(self.lib.tob_vec_scale(self.h, _ptr(v), a, n))
 
     def microbench_fp64(self, kind):
         v = C.c_double()
@@ -198,6 +209,9 @@ class LinearElasticity:
         r = np.empty(self.ctx.ndof_owned)
         check(self.lib.tob_elast_get_rhs(self.h, r.ctypes.data))
         return r
+
+    def SetProfile(self, on=True):
+        check(self.lib.tob_elast_set_profile(self.h, 1 if on else 0))
 
     def stats(self) -> SolveStats:
         s = SolveStats()

@@ -217,6 +217,13 @@ int tob_dev_free(tob_ctx* h, void* p) {
     TOB_CUDA(cudaFree(p));
     return 0;
 }
+int tob_nccl_unique_id(void* out128) {
+    ncclUniqueId id;
+    TOB_NCCL(ncclGetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
 int tob_memcpy(tob_ctx* h, void* dst, const void* src, long long nbytes) {
     auto* c = reinterpret_cast<tob_ctx_impl*>(h);
     TOB_CUDA(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDefault, c->stream));

@@ -19,11 +19,47 @@ static int init_const_slots(tob_ctx_impl* c) {
 int elast_apply(tob_elast_impl* h, const double* u, double* y, int epi, bool mask_in, int kernel, const double* a0,
                 int* nparts) {
     SpmvArgs a;
-    a.u = u; a.y = y; a.E = h->E_st; a.mask = h->mask; a.epi = epi; a.mask_in = mask_in;
     a.kernel = kernel ? kernel : h->opts.spmv_kernel;
+    if (mask_in && a.kernel != SPMV_NAIVE) {
+        // public SpMV on an arbitrary vector: apply N first (inside the solver fixed dofs are exactly 0)
+        TOB_CHECK(vec_pointwise_mult(h->c, h->Z, u, h->NFREE, h->g->nvec));
+        u = h->Z;
+        mask_in = false;
+    }
+    a.u = u; a.y = y; a.E = h->E_st; a.mask = h->mask; a.epi = epi; a.mask_in = mask_in;
     a.a0 = a0;
     h->stats.spmv_calls++;
-    return hex8_spmv(h->c, *h->g, h->op, a, nparts);
+    constexpr int kMaxPairs = 2048;
+    const bool timed = h->profile && h->prof_used < kMaxPairs;
+    if (timed) {
+        if ((int)h->prof_ev.size() < 2 * (h->prof_used + 1)) {
+            cudaEvent_t e0, e1;
+            TOB_CUDA(cudaEventCreate(&e0));
+            TOB_CUDA(cudaEventCreate(&e1));
+            h->prof_ev.push_back(e0);
+            h->prof_ev.push_back(e1);
+        }
+        TOB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_used], h->c->stream));
+    }
+    int rc = hex8_spmv(h->c, *h->g, h->op, a, nparts);
+    if (timed) {
+        TOB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_used + 1], h->c->stream));
+        h->prof_used++;
+    }
+    return rc;
+}
+
+int elast_profile_collect(tob_elast_impl* h) {
+    // called after the solve's final synchronisation: sum the recorded pairs
+    for (int i = 0; i < h->prof_used; i++) {
+        float ms = 0;
+        TOB_CUDA(cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+        TOB_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        h->stats.spmv_seconds += ms * 1e-3;
+        h->stats.spmv_timed++;
+    }
+    h->prof_used = 0;
+    return 0;
 }
 
 int elast_set_density(tob_elast_impl* h, const double* xphys_nat_dev, double Emin, double Emax, double penal) {
@@ -103,6 +139,9 @@ int elast_pcg(tob_elast_impl* h) {
     h->stats.iterations = it;
     h->stats.rel_residual = bnorm > 0 ? rnorm / bnorm : 0.0;
     h->stats.seconds = ms * 1e-3;
+    h->stats.spmv_seconds = 0.0;
+    h->stats.spmv_timed = 0;
+    if (h->profile) TOB_CHECK(elast_profile_collect(h));
     if (o.verbose && c->desc.rank == 0)
         printf("State solver:  iter: %i, rerr.: %e, time: %f\n", it, h->stats.rel_residual, h->stats.seconds);
     return 0;
@@ -224,6 +263,7 @@ void elast_destroy(tob_elast_impl* h) {
     double* vecs[] = {h->U, h->B, h->RHS, h->R, h->P, h->Q, h->Z, h->DINV, h->NFREE, h->xphys_st, h->E_st,
                       h->nat_dof, h->nat_dof2, h->nat_el, h->nat_el2};
     for (auto v : vecs) cudaFree(v);
+    for (auto e : h->prof_ev) cudaEventDestroy(e);
     cudaFree(h->mask);
     hex8_free_operator(h->op);
     delete h;
@@ -399,6 +439,12 @@ int tob_elast_get_rhs(tob_elast* hh, double* rhs) {
     TOB_CHECK(stage_out_begin(h->c, 1, rhs, sizeof(double) * nd, &du));
     TOB_CHECK(stored_to_nat_dof(h->c, *h->g, h->RHS, (double*)du));
     return stage_out_finish(h->c, rhs, du, sizeof(double) * nd);
+}
+int tob_elast_set_profile(tob_elast* hh, int on) {
+    auto* h = reinterpret_cast<tob_elast_impl*>(hh);
+    h->profile = on != 0;
+    h->prof_used = 0;
+    return 0;
 }
 int tob_elast_last_stats(tob_elast* hh, tob_solve_stats* s) {
     auto* h = reinterpret_cast<tob_elast_impl*>(hh);

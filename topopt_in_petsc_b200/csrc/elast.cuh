@@ -26,7 +26,12 @@ struct tob_elast_impl {
     bool have_density = false;
     tob_solve_stats stats{};
     GmgHierarchy* mg = nullptr;
+    // optional per-launch SpMV timing (bench.py roofline): event pairs recorded around each launch
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_used = 0;
 };
+int elast_profile_collect(tob_elast_impl* h);
 
 int elast_create(tob_ctx_impl* c, double nu, const tob_solver_opts* opts, tob_elast_impl** out);
 void elast_destroy(tob_elast_impl* h);

@@ -2,8 +2,9 @@
 //
 // Hot kernel: k_hex8_zmarch.  One CTA owns an (x,y) tile of node columns and marches along z.
 // Every z-step a TMA bulk-tensor load (cp.async.bulk.tensor, mbarrier complete_tx) brings the next
-// nodal plane tile (3 components), the element-modulus tile of the layer below it and the
-// Dirichlet-mask tile into a 4-stage shared-memory ring.  Each thread owns one element column:
+// nodal plane tile (3 components) and the element-modulus tile of the layer below it into a
+// 4-stage shared-memory ring (the byte-wide Dirichlet mask of the own node comes through a plain
+// load issued one step ahead).  Each thread owns one element column:
 // it forms the Walsh-Hadamard "face modes" of the new plane, combines them with the face modes
 // of the previous plane kept in registers, applies the 8 3x3 blocks of the block-diagonalised
 // element matrix scaled by the SIMP modulus, and transforms back stage by stage; partial results
@@ -202,8 +203,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
 constexpr int ZM_STAGES = 4;
 
 struct ZmParams {
-    int nxn, nyn;
-    int px;
+    int nxn, nyn, nzl;
+    int px, pm;
+    long long mstride;
+    const unsigned char* mask;
     long long nstride, pstride;
     int zout0, zout1;  // local node planes written: [zout0, zout1)
     int zchunk;        // planes per CTA along z
@@ -215,25 +218,29 @@ struct ZmParams {
     double* partials;
 };
 
+// TMA tiles are ZM_W = 34 doubles wide: with a non-swizzled tensor map the innermost start
+// coordinate must be 16-byte aligned (measured: odd fp64 origins raise "illegal instruction"), so the
+// box starts at the even column bx*30-2 and thread tx reads column tx+1.
+constexpr int ZM_W = 34;
 template <int TY>
 struct ZmSmem {
     static constexpr int NT = 32 * TY;
-    static constexpr int U_BYTES = 3 * NT * 8;
-    static constexpr int E_BYTES = NT * 8;
-    static constexpr int M_BYTES = NT;
-    static constexpr int STAGE_BYTES = U_BYTES + E_BYTES + M_BYTES;
+    static constexpr int NC = ZM_W * TY;          // doubles per component tile
+    static constexpr int U_BYTES = 3 * NC * 8;
+    static constexpr int E_BYTES = NC * 8;
+    static constexpr int STAGE_BYTES = U_BYTES + E_BYTES;
     static constexpr int XCH_BYTES = 2 * 6 * NT * 8;
     static constexpr int BAR_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES;
     static constexpr int TOTAL = BAR_OFF + ZM_STAGES * 8 + 128;
 };
 
-template <int TY, int EPI, bool MASK_IN>
+template <int TY, int EPI>
 __global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
 k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
-              const __grid_constant__ CUtensorMap tmM, const __grid_constant__ Hex8Blocks KB,
-              const __grid_constant__ ZmParams P) {
+              const __grid_constant__ Hex8Blocks KB, const __grid_constant__ ZmParams P) {
     using L = ZmSmem<TY>;
     constexpr int NT = L::NT;
+    constexpr int NC = L::NC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double red[32];
     double* xch = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES);
@@ -264,9 +271,13 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const int p = pfirst + pidx;
             mbar_expect_tx(&bars[s], L::STAGE_BYTES);
-            tma_load_4d(st, &tmU, &bars[s], i0, j0, 0, p);
-            tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0, j0, p - 1);
-            tma_load_3d(st + L::U_BYTES + L::E_BYTES, &tmM, &bars[s], i0, j0, p);
+            tma_load_4d(st, &tmU, &bars[s], i0 - 1, j0, 0, p);
+            tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
+        };
+        // Dirichlet mask byte of my own node on local plane p (0 outside the grid)
+        const bool innode = (i >= 0) && (i < P.nxn) && (j >= 0) && (j < P.nyn);
+        auto load_mask = [&](int p) -> unsigned {
+            return (innode && p >= 0 && p < P.nzl) ? (unsigned)P.mask[(long long)p * P.mstride + (long long)j * P.pm + i] : 0u;
         };
         if (tid == 0)
             for (int s = 0; s < ZM_STAGES && s < nplanes; s++) issue(s);
@@ -281,25 +292,15 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 #pragma unroll
             for (int f = 0; f < 4; f++) { fprev[c][f] = 0.0; upacc[c][f] = 0.0; }
         }
-        const int o = ty * 32 + tx;
+        const int o = ty * ZM_W + tx + 1;  // my node inside a component tile
+        const int o2 = ty * 32 + tx;       // my slot in the exchange buffers
 
         // face modes of one plane tile: X stage on rows j and j+1, then Y stage
         auto face_modes = [&](const unsigned char* st, double (&fm)[3][4]) {
             const double* su = reinterpret_cast<const double*>(st);
-            unsigned m00 = 0, m10 = 0, m01 = 0, m11 = 0;
-            if (MASK_IN) {
-                const unsigned char* sm = st + L::U_BYTES + L::E_BYTES;
-                m00 = sm[o]; m10 = sm[o + 1]; m01 = sm[o + 32]; m11 = sm[o + 33];
-            }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                double a = su[c * NT + o], b = su[c * NT + o + 1], cc = su[c * NT + o + 32], d = su[c * NT + o + 33];
-                if (MASK_IN) {
-                    if (m00 & (1u << c)) a = 0.0;
-                    if (m10 & (1u << c)) b = 0.0;
-                    if (m01 & (1u << c)) cc = 0.0;
-                    if (m11 & (1u << c)) d = 0.0;
-                }
+                const double a = su[c * NC + o], b = su[c * NC + o + 1], cc = su[c * NC + o + ZM_W], d = su[c * NC + o + ZM_W + 1];
                 const double s0 = a + b, d0 = a - b, s1 = cc + d, d1 = cc - d;
                 fm[c][0] = s0 + s1;
                 fm[c][1] = d0 + d1;
@@ -314,8 +315,8 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             const unsigned char* st = smem_raw;
             const double* su = reinterpret_cast<const double*>(st);
 #pragma unroll
-            for (int c = 0; c < 3; c++) uown[c] = su[c * NT + o];
-            mown = (st + L::U_BYTES + L::E_BYTES)[o];
+            for (int c = 0; c < 3; c++) uown[c] = su[c * NC + o];
+            mown = load_mask(pfirst);
             if (compute) face_modes(st, fprev);
             __syncthreads();
             if (tid == 0 && ZM_STAGES < nplanes) issue(ZM_STAGES);
@@ -327,12 +328,12 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             const int pidx = t + 1;
             const int s = pidx % ZM_STAGES;
             const unsigned char* st = smem_raw + s * L::STAGE_BYTES;
+            const unsigned mnew = load_mask(pfirst + pidx);  // consumed one step later
             mbar_wait(&bars[s], (pidx / ZM_STAGES) & 1);
             const double* su = reinterpret_cast<const double*>(st);
             double unew[3];
 #pragma unroll
-            for (int c = 0; c < 3; c++) unew[c] = su[c * NT + o];
-            const unsigned mnew = (st + L::U_BYTES + L::E_BYTES)[o];
+            for (int c = 0; c < 3; c++) unew[c] = su[c * NC + o];
 
             double ex0[3][2];  // edge (row j) contributions of my face
             double* xw = xch + (t & 1) * 6 * NT;
@@ -392,7 +393,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 #pragma unroll
                     for (int ma = 0; ma < 2; ma++) {
                         ex0[c][ma] = ht[c][ma] + ht[c][ma + 2];
-                        xw[(2 * c + ma) * NT + o] = ht[c][ma] - ht[c][ma + 2];
+                        xw[(2 * c + ma) * NT + o2] = ht[c][ma] - ht[c][ma + 2];
                     }
             } else {
 #pragma unroll
@@ -407,8 +408,8 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             for (int c = 0; c < 3; c++) {
                 double e0 = ex0[c][0], e1 = ex0[c][1];
                 if (ty >= 1) {
-                    e0 += xw[(2 * c + 0) * NT + o - 32];
-                    e1 += xw[(2 * c + 1) * NT + o - 32];
+                    e0 += xw[(2 * c + 0) * NT + o2 - 32];
+                    e1 += xw[(2 * c + 1) * NT + o2 - 32];
                 }
                 v[c] = e0 + e1;
                 vr[c] = e0 - e1;
@@ -468,30 +469,24 @@ static int encode_map(tob_ctx_impl* c, CUtensorMap* tm, CUtensorMapDataType dt, 
     return 0;
 }
 
-template <int TY, int EPI, bool MASK_IN>
+template <int TY, int EPI>
 static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     using L = ZmSmem<TY>;
-    CUtensorMap tmU, tmE, tmM;
+    CUtensorMap tmU, tmE;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, 3, (cuuint64_t)g.nzl()};
         cuuint64_t str[3] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.nstride * 8, (cuuint64_t)g.pstride * 8};
-        cuuint32_t box[4] = {32, (cuuint32_t)TY, 3, 1};
+        cuuint32_t box[4] = {ZM_W, (cuuint32_t)TY, 3, 1};
         TOB_CHECK(encode_map(c, &tmU, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, a.u, dims, str, box));
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)g.nex, (cuuint64_t)g.ney, (cuuint64_t)g.nzle()};
         cuuint64_t str[2] = {(cuuint64_t)g.pe * 8, (cuuint64_t)g.estride * 8};
-        cuuint32_t box[3] = {32, (cuuint32_t)TY, 1};
+        cuuint32_t box[3] = {ZM_W, (cuuint32_t)TY, 1};
         TOB_CHECK(encode_map(c, &tmE, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, a.E, dims, str, box));
     }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, (cuuint64_t)g.nzl()};
-        cuuint64_t str[2] = {(cuuint64_t)g.pm, (cuuint64_t)g.mstride};
-        cuuint32_t box[3] = {32, (cuuint32_t)TY, 1};
-        TOB_CHECK(encode_map(c, &tmM, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, a.mask, dims, str, box));
-    }
     ZmParams P;
-    P.nxn = g.nxn; P.nyn = g.nyn; P.px = g.px; P.nstride = g.nstride; P.pstride = g.pstride;
+    P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.px = g.px; P.pm = g.pm; P.mstride = g.mstride; P.mask = a.mask; P.nstride = g.nstride; P.pstride = g.pstride;
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1();
     P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
     const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, TY - 2);
@@ -505,13 +500,13 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
     if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
-    auto kern = k_hex8_zmarch<TY, EPI, MASK_IN>;
+    auto kern = k_hex8_zmarch<TY, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, tmM, op.blocks, P);
+    kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, op.blocks, P);
     c->launches++;
     TOB_KERNEL_CHECK();
     if (nparts) *nparts = (EPI == EPI_DOT || EPI == EPI_RESID) ? gx * gy * nch : 0;
@@ -520,25 +515,18 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
 
 template <int TY>
 static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
-    if (a.mask_in) {
-        switch (a.epi) {
-            case EPI_Y: return launch_zm<TY, EPI_Y, true>(c, g, op, a, nparts);
-            case EPI_DOT: return launch_zm<TY, EPI_DOT, true>(c, g, op, a, nparts);
-            case EPI_RESID: return launch_zm<TY, EPI_RESID, true>(c, g, op, a, nparts);
-            default: return launch_zm<TY, EPI_CHEB, true>(c, g, op, a, nparts);
-        }
-    }
     switch (a.epi) {
-        case EPI_Y: return launch_zm<TY, EPI_Y, false>(c, g, op, a, nparts);
-        case EPI_DOT: return launch_zm<TY, EPI_DOT, false>(c, g, op, a, nparts);
-        case EPI_RESID: return launch_zm<TY, EPI_RESID, false>(c, g, op, a, nparts);
-        default: return launch_zm<TY, EPI_CHEB, false>(c, g, op, a, nparts);
+        case EPI_Y: return launch_zm<TY, EPI_Y>(c, g, op, a, nparts);
+        case EPI_DOT: return launch_zm<TY, EPI_DOT>(c, g, op, a, nparts);
+        case EPI_RESID: return launch_zm<TY, EPI_RESID>(c, g, op, a, nparts);
+        default: return launch_zm<TY, EPI_CHEB>(c, g, op, a, nparts);
     }
 }
 
 int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     if (nparts) *nparts = 0;
     int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM8 : a.kernel;
+    if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
     if (kernel == SPMV_NAIVE) {
         if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");
         dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());

@@ -34,7 +34,7 @@ struct SpmvArgs {
     const double* E = nullptr;           // stored element modulus field
     const unsigned char* mask = nullptr; // stored Dirichlet mask
     int epi = EPI_Y;
-    bool mask_in = true;                 // apply N to the input (false inside the solver: fixed dofs are exactly 0)
+    bool mask_in = true;                 // input still needs N applied (naive kernel only; z-march callers pre-mask)
     int kernel = SPMV_AUTO;
     // epilogue operands (stored layout)
     const double* a0 = nullptr;          // RESID/CHEB: b

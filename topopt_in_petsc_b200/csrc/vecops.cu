@@ -292,3 +292,17 @@ int vec_fill(tob_ctx_impl* c, double* y, double v, long long n) {
 }
 
 }  // namespace tob
+
+extern "C" int tob_vec_scale(tob_ctx* ctx, double* v, double a, long long n) {
+    using namespace tob;
+    auto* c = reinterpret_cast<tob_ctx_impl*>(ctx);
+    const void* din;
+    TOB_CHECK(stage_in(c, 0, v, sizeof(double) * n, &din));
+    double* d = (double*)din;
+    TOB_CHECK(vec_axpby(c, d, d, a, 0.0, n));
+    if ((void*)d != (void*)v) {
+        TOB_CUDA(cudaMemcpyAsync(v, d, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        TOB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
