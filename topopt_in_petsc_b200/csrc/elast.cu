@@ -20,7 +20,9 @@ int elast_apply(tob_elast_impl* h, const double* u, double* y, int epi, bool mas
                 int* nparts) {
     SpmvArgs a;
     a.kernel = kernel ? kernel : h->opts.spmv_kernel;
+    const double* u_orig = nullptr;
     if (mask_in && a.kernel != SPMV_NAIVE) {
+        u_orig = u;
         // public SpMV on an arbitrary vector: apply N first (inside the solver fixed dofs are exactly 0)
         TOB_CHECK(vec_pointwise_mult(h->c, h->Z, u, h->NFREE, h->g->nvec));
         u = h->Z;
@@ -42,6 +44,8 @@ int elast_apply(tob_elast_impl* h, const double* u, double* y, int epi, bool mas
         TOB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_used], h->c->stream));
     }
     int rc = hex8_spmv(h->c, *h->g, h->op, a, nparts);
+    // pre-masked input: the kernel returned 0 on clamped dofs, the operator wants (I-N) u there
+    if (rc == 0 && u_orig) rc = vec_restore_fixed(h->c, y + h->g->own_off, u_orig + h->g->own_off, h->NFREE + h->g->own_off, h->g->own_len);
     if (timed) {
         TOB_CUDA(cudaEventRecord(h->prof_ev[2 * h->prof_used + 1], h->c->stream));
         h->prof_used++;

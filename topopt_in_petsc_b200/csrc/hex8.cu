@@ -222,28 +222,34 @@ struct ZmParams {
 // coordinate must be 16-byte aligned (measured: odd fp64 origins raise "illegal instruction"), so the
 // box starts at the even column bx*30-2 and thread tx reads column tx+1.
 constexpr int ZM_W = 34;
-template <int TY>
+template <int TY, bool SMEM_STATE = true>
 struct ZmSmem {
     static constexpr int NT = 32 * TY;
     static constexpr int NC = ZM_W * TY;          // doubles per component tile
-    static constexpr int U_BYTES = 3 * NC * 8;
-    static constexpr int E_BYTES = NC * 8;
+    static constexpr int U_BYTES = (3 * NC * 8 + 127) / 128 * 128;  // TMA destinations must be 128-byte aligned
+    static constexpr int E_BYTES = (NC * 8 + 127) / 128 * 128;
+    static constexpr int TX_BYTES = 4 * NC * 8;                     // bytes the two TMA loads deliver per stage
     static constexpr int STAGE_BYTES = U_BYTES + E_BYTES;
     static constexpr int XCH_BYTES = 2 * 6 * NT * 8;
-    static constexpr int BAR_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES;
+    static constexpr int UP_BYTES = SMEM_STATE ? 24 * NT * 8 : 0;  // carried state when kept out of registers
+    static constexpr int BAR_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;
     static constexpr int TOTAL = BAR_OFF + ZM_STAGES * 8 + 128;
 };
 
-template <int TY, int EPI>
+// SMEM_STATE: the 24 doubles carried from one z-step to the next (lower-face modes + upper-face
+// contributions) live in shared memory (lets two 256-thread CTAs share an SM at 128 registers) or in
+// registers (one CTA per SM with a larger register budget; less shared-memory traffic).
+template <int TY, int EPI, bool SMEM_STATE>
 __global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
 k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
               const __grid_constant__ Hex8Blocks KB, const __grid_constant__ ZmParams P) {
-    using L = ZmSmem<TY>;
+    using L = ZmSmem<TY, SMEM_STATE>;
     constexpr int NT = L::NT;
     constexpr int NC = L::NC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double red[32];
     double* xch = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES);
+    double* ups = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES + L::XCH_BYTES) + (threadIdx.x);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
 
     const int tid = threadIdx.x;
@@ -270,7 +276,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             const int s = pidx % ZM_STAGES;
             unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const int p = pfirst + pidx;
-            mbar_expect_tx(&bars[s], L::STAGE_BYTES);
+            mbar_expect_tx(&bars[s], L::TX_BYTES);
             tma_load_4d(st, &tmU, &bars[s], i0 - 1, j0, 0, p);
             tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
         };
@@ -282,15 +288,13 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         if (tid == 0)
             for (int s = 0; s < ZM_STAGES && s < nplanes; s++) issue(s);
 
-        double fprev[3][4];  // face modes of the lower plane of the current element
-        double upacc[3][4];  // upper-face contributions of the previous element
-        double uown[3];      // own node value on the plane being completed
+        double* fps = ups + 12 * NT;  // face modes of the lower plane of the current element
+        double fpr[12], upr[12];      // register copies of the carried state (SMEM_STATE == false)
         unsigned mown = 0;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            uown[c] = 0.0;
-#pragma unroll
-            for (int f = 0; f < 4; f++) { fprev[c][f] = 0.0; upacc[c][f] = 0.0; }
+        for (int k = 0; k < 12; k++) {
+            if (SMEM_STATE) { ups[k * NT] = 0.0; fps[k * NT] = 0.0; }
+            fpr[k] = 0.0; upr[k] = 0.0;
         }
         const int o = ty * ZM_W + tx + 1;  // my node inside a component tile
         const int o2 = ty * 32 + tx;       // my slot in the exchange buffers
@@ -313,13 +317,18 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         {
             mbar_wait(&bars[0], 0);
             const unsigned char* st = smem_raw;
-            const double* su = reinterpret_cast<const double*>(st);
-#pragma unroll
-            for (int c = 0; c < 3; c++) uown[c] = su[c * NC + o];
             mown = load_mask(pfirst);
-            if (compute) face_modes(st, fprev);
-            __syncthreads();
-            if (tid == 0 && ZM_STAGES < nplanes) issue(ZM_STAGES);
+            if (compute) {
+                double f0[3][4];
+                face_modes(st, f0);
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int f = 0; f < 4; f++) {
+                        if (SMEM_STATE) fps[(4 * c + f) * NT] = f0[c][f];
+                        else fpr[4 * c + f] = f0[c][f];
+                    }
+            }
         }
 
         // ---- march: step t handles element layer e = pfirst + t, upper plane pfirst + t + 1 -----
@@ -330,10 +339,6 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             const unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const unsigned mnew = load_mask(pfirst + pidx);  // consumed one step later
             mbar_wait(&bars[s], (pidx / ZM_STAGES) & 1);
-            const double* su = reinterpret_cast<const double*>(st);
-            double unew[3];
-#pragma unroll
-            for (int c = 0; c < 3; c++) unew[c] = su[c * NC + o];
 
             double ex0[3][2];  // edge (row j) contributions of my face
             double* xw = xch + (t & 1) * 6 * NT;
@@ -347,9 +352,11 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 for (int c = 0; c < 3; c++)
 #pragma unroll
                     for (int f = 0; f < 4; f++) {
-                        uh[c][f] = fprev[c][f] + fnew[c][f];
-                        uh[c][4 + f] = fprev[c][f] - fnew[c][f];
-                        fprev[c][f] = fnew[c][f];
+                        const double fl = SMEM_STATE ? fps[(4 * c + f) * NT] : fpr[4 * c + f];
+                        uh[c][f] = fl + fnew[c][f];
+                        uh[c][4 + f] = fl - fnew[c][f];
+                        if (SMEM_STATE) fps[(4 * c + f) * NT] = fnew[c][f];
+                        else fpr[4 * c + f] = fnew[c][f];
                     }
                 // 8 blocks of 3x3, scaled by the modulus
                 double yh[3][8];
@@ -384,8 +391,9 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 for (int c = 0; c < 3; c++)
 #pragma unroll
                     for (int f = 0; f < 4; f++) {
-                        ht[c][f] = (yh[c][f] + yh[c][4 + f]) + upacc[c][f];
-                        upacc[c][f] = yh[c][f] - yh[c][4 + f];
+                        ht[c][f] = (yh[c][f] + yh[c][4 + f]) + (SMEM_STATE ? ups[(4 * c + f) * NT] : upr[4 * c + f]);
+                        if (SMEM_STATE) ups[(4 * c + f) * NT] = yh[c][f] - yh[c][4 + f];
+                        else upr[4 * c + f] = yh[c][f] - yh[c][4 + f];
                     }
                 // Y' stage: row j part stays, row j+1 part goes to the thread above
 #pragma unroll
@@ -400,7 +408,8 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 for (int c = 0; c < 3; c++) { ex0[c][0] = 0.0; ex0[c][1] = 0.0; }
             }
             __syncthreads();
-            if (tid == 0 && pidx + ZM_STAGES < nplanes) issue(pidx + ZM_STAGES);
+            // the ring slot of plane pidx-2 is free now (plane pidx-1 is still read below for the output)
+            if (tid == 0 && pidx >= 2 && pidx - 2 + ZM_STAGES < nplanes) issue(pidx - 2 + ZM_STAGES);
 
             // edge totals, X' stage, node totals
             double v[3], vr[3];
@@ -419,16 +428,18 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 
             const int e = pfirst + t;  // node plane completed by this step
             if (outthr && e >= z0) {
+                const double* sl = reinterpret_cast<const double*>(smem_raw + (t % ZM_STAGES) * L::STAGE_BYTES);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const long long idx = e * P.pstride + c * P.nstride + (long long)j * P.px + i;
                     const bool fixed = (mown >> c) & 1u;
-                    const double au = fixed ? uown[c] : v[c];
+                    const double uo = sl[c * NC + o];  // own nodal value on plane e (still in the ring)
+                    const double au = fixed ? uo : v[c];
                     if (EPI == EPI_Y) {
                         P.y[idx] = au;
                     } else if (EPI == EPI_DOT) {
                         P.y[idx] = au;
-                        part = fma(uown[c], au, part);
+                        part = fma(uo, au, part);
                     } else if (EPI == EPI_RESID) {
                         const double r = P.a0[idx] - au;
                         P.y[idx] = r;
@@ -437,12 +448,10 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         const double r = P.a0[idx] - au;
                         const double dn = P.s0 * P.o1[idx] + P.s1 * P.a1[idx] * r;
                         P.o1[idx] = dn;
-                        P.y[idx] = uown[c] + dn;
+                        P.y[idx] = uo + dn;
                     }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 3; c++) uown[c] = unew[c];
             mown = mnew;
         }
     }
@@ -471,7 +480,8 @@ static int encode_map(tob_ctx_impl* c, CUtensorMap* tm, CUtensorMapDataType dt, 
 
 template <int TY, int EPI>
 static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
-    using L = ZmSmem<TY>;
+    constexpr bool SMEM_STATE = (TY != 12);
+    using L = ZmSmem<TY, SMEM_STATE>;
     CUtensorMap tmU, tmE;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, 3, (cuuint64_t)g.nzl()};
@@ -500,7 +510,7 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
     if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
-    auto kern = k_hex8_zmarch<TY, EPI>;
+    auto kern = k_hex8_zmarch<TY, EPI, SMEM_STATE>;
     static bool attr_set = false;
     if (!attr_set) {
         TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -538,6 +548,7 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
         return 0;
     }
     if (kernel == SPMV_ZM16) return dispatch_zm<16>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM12) return dispatch_zm<12>(c, g, op, a, nparts);
     return dispatch_zm<8>(c, g, op, a, nparts);
 }
 

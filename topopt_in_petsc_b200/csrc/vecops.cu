@@ -279,6 +279,19 @@ int vec_pointwise_mult(tob_ctx_impl* c, double* y, const double* a, const double
     TOB_KERNEL_CHECK();
     return 0;
 }
+// y = free ? y : u   (restores the (I-N) u part of the Dirichlet operator on clamped dofs)
+__global__ void __launch_bounds__(kFlatThreads) k_restore_fixed(double* __restrict__ y, const double* __restrict__ u,
+                                                                const double* __restrict__ nf, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (nf[i] == 0.0) y[i] = u[i];
+}
+int vec_restore_fixed(tob_ctx_impl* c, double* y, const double* u, const double* nf, long long n) {
+    if (n <= 0) return 0;
+    k_restore_fixed<<<flat_grid(c, n), kFlatThreads, 0, c->stream>>>(y, u, nf, n);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
 __global__ void __launch_bounds__(kFlatThreads) k_fill(double* __restrict__ y, double v, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = v;

@@ -15,4 +15,5 @@ int pcg_update_p(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* z
 int vec_axpby(tob_ctx_impl* c, double* y, const double* x, double a, double b, long long n);
 int vec_pointwise_mult(tob_ctx_impl* c, double* y, const double* a, const double* b, long long n);
 int vec_fill(tob_ctx_impl* c, double* y, double v, long long n);
+int vec_restore_fixed(tob_ctx_impl* c, double* y, const double* u, const double* nf, long long n);
 }  // namespace tob
