@@ -184,6 +184,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ void lds2(double& a, double& b, uint32_t addr) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -232,7 +235,8 @@ struct ZmSmem {
     static constexpr int STAGE_BYTES = U_BYTES + E_BYTES;
     static constexpr int XCH_BYTES = 2 * 6 * NT * 8;
     static constexpr int UP_BYTES = SMEM_STATE ? 24 * NT * 8 : 0;  // carried state when kept out of registers
-    static constexpr int BAR_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;
+    static constexpr int KB_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;  // 48 block constants
+    static constexpr int BAR_OFF = KB_OFF + 48 * 8;
     static constexpr int TOTAL = BAR_OFF + ZM_STAGES * 8 + 128;
 };
 
@@ -251,6 +255,10 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
     double* xch = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES);
     double* ups = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES + L::XCH_BYTES) + (threadIdx.x);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+    // symmetric 3x3 blocks, 6 unique entries each (b00 b01 b02 b11 b12 b22), read back with broadcast
+    // ld.shared.v2.f64: keeping 72 constants in uniform registers made the loop issue-bound.
+    double* kbs = reinterpret_cast<double*>(smem_raw + L::KB_OFF);
+    const uint32_t kb_addr = smem_u32(kbs);
 
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;
@@ -265,6 +273,11 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
     double part = 0.0;
 
     if (z0 < z1) {
+        if (tid < 48) {
+            const int rho = tid / 6, k = tid % 6;
+            const int r = k < 3 ? 0 : (k < 5 ? 1 : 2), cc = k < 3 ? k : (k < 5 ? k - 2 : 2);
+            kbs[tid] = KB.b[rho][3 * r + cc];
+        }
         if (tid == 0) {
             for (int s = 0; s < ZM_STAGES; s++) mbar_init(&bars[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -358,28 +371,32 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         if (SMEM_STATE) fps[(4 * c + f) * NT] = fnew[c][f];
                         else fpr[4 * c + f] = fnew[c][f];
                     }
-                // 8 blocks of 3x3, scaled by the modulus
+                // 8 symmetric blocks of 3x3, scaled by the modulus (rho = 1,2,4 have a zero row/column)
                 double yh[3][8];
 #pragma unroll
                 for (int rho = 0; rho < 8; rho++) {
                     const double in0 = uh[0][rho ^ 1], in1 = uh[1][rho ^ 2], in2 = uh[2][rho ^ 4];
+                    double b00, b01, b02, b11, b12, b22;
+                    lds2(b00, b01, kb_addr + rho * 48);
+                    lds2(b02, b11, kb_addr + rho * 48 + 16);
+                    lds2(b12, b22, kb_addr + rho * 48 + 32);
                     double o0, o1, o2;
                     if (rho == 1) {
                         o0 = 0.0;
-                        o1 = KB.b[1][4] * in1 + KB.b[1][5] * in2;
-                        o2 = KB.b[1][7] * in1 + KB.b[1][8] * in2;
+                        o1 = b11 * in1 + b12 * in2;
+                        o2 = b12 * in1 + b22 * in2;
                     } else if (rho == 2) {
                         o1 = 0.0;
-                        o0 = KB.b[2][0] * in0 + KB.b[2][2] * in2;
-                        o2 = KB.b[2][6] * in0 + KB.b[2][8] * in2;
+                        o0 = b00 * in0 + b02 * in2;
+                        o2 = b02 * in0 + b22 * in2;
                     } else if (rho == 4) {
                         o2 = 0.0;
-                        o0 = KB.b[4][0] * in0 + KB.b[4][1] * in1;
-                        o1 = KB.b[4][3] * in0 + KB.b[4][4] * in1;
+                        o0 = b00 * in0 + b01 * in1;
+                        o1 = b01 * in0 + b11 * in1;
                     } else {
-                        o0 = KB.b[rho][0] * in0 + KB.b[rho][1] * in1 + KB.b[rho][2] * in2;
-                        o1 = KB.b[rho][3] * in0 + KB.b[rho][4] * in1 + KB.b[rho][5] * in2;
-                        o2 = KB.b[rho][6] * in0 + KB.b[rho][7] * in1 + KB.b[rho][8] * in2;
+                        o0 = b00 * in0 + b01 * in1 + b02 * in2;
+                        o1 = b01 * in0 + b11 * in1 + b12 * in2;
+                        o2 = b02 * in0 + b12 * in1 + b22 * in2;
                     }
                     yh[0][rho ^ 1] = Ee * o0;
                     yh[1][rho ^ 2] = Ee * o1;
@@ -478,9 +495,8 @@ static int encode_map(tob_ctx_impl* c, CUtensorMap* tm, CUtensorMapDataType dt, 
     return 0;
 }
 
-template <int TY, int EPI>
+template <int TY, int EPI, bool SMEM_STATE>
 static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
-    constexpr bool SMEM_STATE = (TY != 12);
     using L = ZmSmem<TY, SMEM_STATE>;
     CUtensorMap tmU, tmE;
     {
@@ -501,12 +517,23 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
     const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, TY - 2);
     const int nz = P.zout1 - P.zout0;
-    // z-chunks: enough CTAs for >= ~3 waves, but chunks of at least 8 planes (each chunk recomputes one layer)
+    // z-chunks: every chunk recomputes one element layer and pays a prologue, and the grid runs in waves
+    // of ctas_per_wave CTAs (ncu: with 3.16 waves the SMs idled 21% of the time) -> pick the chunk count
+    // that minimises  waves * (planes per chunk + overhead).
     const int ctas_per_wave = c->num_sms * ((TY <= 8) ? 2 : 1);
-    int nch = div_up(3LL * ctas_per_wave, (long long)gx * gy);
-    int max_ch = nz / 8 > 0 ? nz / 8 : 1;
-    if (nch > max_ch) nch = max_ch;
-    if (nch < 1) nch = 1;
+    int nch = 1;
+    {
+        double best = 1e300;
+        const long long tiles = (long long)gx * gy;
+        for (int k = 1; k <= nz; k++) {
+            const int zc = div_up(nz, k);
+            if (zc < 4 && k > 1) break;
+            const int kk = div_up(nz, zc);
+            const double waves = ceil((double)(tiles * kk) / ctas_per_wave);
+            const double cost = waves * (zc + 3.0);
+            if (cost < best * 0.999) { best = cost; nch = kk; }
+        }
+    }
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
     if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
@@ -523,13 +550,13 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     return 0;
 }
 
-template <int TY>
+template <int TY, bool SMEM_STATE>
 static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     switch (a.epi) {
-        case EPI_Y: return launch_zm<TY, EPI_Y>(c, g, op, a, nparts);
-        case EPI_DOT: return launch_zm<TY, EPI_DOT>(c, g, op, a, nparts);
-        case EPI_RESID: return launch_zm<TY, EPI_RESID>(c, g, op, a, nparts);
-        default: return launch_zm<TY, EPI_CHEB>(c, g, op, a, nparts);
+        case EPI_Y: return launch_zm<TY, EPI_Y, SMEM_STATE>(c, g, op, a, nparts);
+        case EPI_DOT: return launch_zm<TY, EPI_DOT, SMEM_STATE>(c, g, op, a, nparts);
+        case EPI_RESID: return launch_zm<TY, EPI_RESID, SMEM_STATE>(c, g, op, a, nparts);
+        default: return launch_zm<TY, EPI_CHEB, SMEM_STATE>(c, g, op, a, nparts);
     }
 }
 
@@ -547,9 +574,10 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
         TOB_KERNEL_CHECK();
         return 0;
     }
-    if (kernel == SPMV_ZM16) return dispatch_zm<16>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM12) return dispatch_zm<12>(c, g, op, a, nparts);
-    return dispatch_zm<8>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16) return dispatch_zm<16, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM12) return dispatch_zm<12, false>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM8R) return dispatch_zm<8, false>(c, g, op, a, nparts);
+    return dispatch_zm<8, true>(c, g, op, a, nparts);
 }
 
 // ---------------------------------------------------------------------------------------
