@@ -50,7 +50,8 @@ typedef struct tob_solver_opts {
     int check_every;     /* host convergence check cadence (iterations) */
     int cheb_degree;     /* Chebyshev-Jacobi smoothing steps per sweep (reference: GMRES(4)+SOR, 4 its) */
     int coarse_its;      /* coarse-grid PCG iteration cap (reference: GMRES(30)+SOR, 30 its) */
-    int spmv_kernel;     /* 0 = auto (z-march WHT/TMA), 1 = naive dense gather (cross-check), 2 = z-march TY=8, 3 = z-march TY=16 */
+    int spmv_kernel;     /* 0 = auto (z-march TY=8, register state), 1 = naive dense gather (cross-check), 2/3 = z-march TY=8/16 with
+                            shared-memory state, 4/5 = z-march TY=12/8 with register state */
     int verbose;
 } tob_solver_opts;
 

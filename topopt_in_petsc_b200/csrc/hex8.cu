@@ -562,7 +562,7 @@ static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& 
 
 int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     if (nparts) *nparts = 0;
-    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM8 : a.kernel;
+    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM8R : a.kernel;
     if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
     if (kernel == SPMV_NAIVE) {
         if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");
