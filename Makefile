@@ -19,7 +19,17 @@ SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(SRCS))
 LIB       := topopt_in_petsc_b200/libtopopt_b200.so
 
-all: $(LIB)
+HOST      := topopt_in_petsc_b200/host
+HOSTSRC   := $(HOST)/petsc_shim.cc $(HOST)/TopOpt.cc $(HOST)/LinearElasticity.cc $(HOST)/Filter.cc $(HOST)/MPIIO.cc
+DRIVER    := $(HOST)/topopt_b200
+
+all: $(LIB) $(DRIVER)
+
+# the product's own driver: B200 classes + device MMA flavour behind the reference's class surfaces
+$(DRIVER): $(HOST)/topopt_b200_main.cc $(HOST)/mma_device/MMA.cc $(HOSTSRC) $(wildcard $(HOST)/*.h $(HOST)/include/*.h $(HOST)/mma_device/*.h) $(LIB)
+	g++ -O2 -std=c++17 -I$(HOST)/mma_device -I$(HOST)/include -I$(HOST) -I/usr/local/cuda/include -o $@ \
+	    $(HOST)/topopt_b200_main.cc $(HOST)/mma_device/MMA.cc $(HOSTSRC) \
+	    -Ltopopt_in_petsc_b200 -ltopopt_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/..' -Wl,-rpath,/usr/local/cuda/lib64
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/topopt_b200.h
 	@mkdir -p $(BUILD)
@@ -29,6 +39,6 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) $(NCCL_LINK)
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(DRIVER)
 
 .PHONY: all clean

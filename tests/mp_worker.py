@@ -1,0 +1,84 @@
+"""Worker for tests/test_multigpu_gpu.py (launched by torchrun, one rank per GPU)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from topopt_in_petsc_b200 import Context, Filter, LinearElasticity, MMA, nccl_unique_id, solver_opts  # noqa: E402
+import topopt_oracle as o  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+if rank == 0:
+    idt = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+dist.broadcast(idt, 0)
+shape = (21, 13, 19)
+g = o.Grid(*shape)
+ctx = Context(*shape, rank=rank, nranks=world, device=local, nccl_id=bytes(idt.cpu().tolist()))
+nex, ney = g.nex, g.ney
+e0, e1 = ctx.ke0 * nex * ney, ctx.ke1 * nex * ney
+d0, d1 = 3 * ctx.kn0 * g.nxn * g.nyn, 3 * ctx.kn1 * g.nxn * g.nyn
+assert ctx.nel_owned == e1 - e0 and ctx.ndof_owned == d1 - d0 and ctx.nel == g.nel
+rng = np.random.default_rng(3)
+x = rng.uniform(0.05, 1.0, g.nel)
+u = rng.uniform(-1, 1, g.ndof)
+KE = o.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+N, RHS = o.cantilever_bc_load(g)
+E = o.simp_modulus(x, 1e-9, 1.0, 3.0)
+# SpMV
+phys = LinearElasticity(ctx, opts=solver_opts(rtol=1e-11, maxits=50000))
+phys.SetDensity(x[e0:e1].copy(), 1e-9, 1.0, 3.0)
+y = phys.SpMV(u[d0:d1].copy())
+yref = o.spmv_matrix_free(g, KE, E, N, u)
+assert np.abs(y - yref[d0:d1]).max() <= 1e-12 * np.abs(yref).max(), "spmv"
+# solve + objective + sensitivities
+K = o.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N)
+import scipy.sparse.linalg as spla
+U = spla.spsolve(K.tocsc(), N * RHS)
+fx0, gx0, df0, dg0 = o.objective_sens(g, KE, U, x, 1e-9, 1.0, 3.0, 0.12)
+df, dg = np.empty(ctx.nel_owned), np.empty(ctx.nel_owned)
+fx, gx = phys.ComputeObjectiveConstraintsSensitivities(df, dg, x[e0:e1].copy(), 1e-9, 1.0, 3.0, 0.12)
+assert abs(fx - fx0) <= 1e-7 * abs(fx0) and abs(gx - gx0) <= 1e-12, ("obj", fx, fx0)
+assert np.abs(df - df0[e0:e1]).max() <= 1e-6 * np.abs(df0).max(), "sens"
+assert np.abs(phys.GetStateField() - U[d0:d1]).max() <= 1e-6 * np.abs(U).max(), "state"
+# filter (2-cell radius so ghost layers matter)
+fo = o.FilterOracle(g, 1, 0.25)
+flt = Filter(ctx, 1, 0.25)
+xt, xp = np.empty(ctx.nel_owned), np.empty(ctx.nel_owned)
+flt.FilterProject(x[e0:e1].copy(), xt, xp, True, 4.0, 0.3)
+xt0, xp0 = fo.filter_project(x, True, 4.0, 0.3)
+assert np.abs(xt - xt0[e0:e1]).max() <= 1e-13 and np.abs(xp - xp0[e0:e1]).max() <= 1e-13, "filter"
+gf, gg = df0[e0:e1].copy(), dg0[e0:e1].copy()
+flt.Gradients(x[e0:e1].copy(), xt, gf, 1, [gg], True, 4.0, 0.3)
+gf0, gg0 = fo.gradients(x, xt0, df0, [dg0], True, 4.0, 0.3)
+assert np.abs(gf - gf0[e0:e1]).max() <= 1e-12 * np.abs(gf0).max(), "filter grad"
+assert abs(flt.GetMND(xp) - o.mnd(xp0)) <= 1e-13, "mnd"
+# MMA
+mo, mg = o.MMAOracle(g.nel, 1), MMA(ctx, 1)
+xm = np.full(g.nel, 0.3)
+for it in range(4):
+    c0 = np.random.default_rng(10 + it).uniform(0.5, 2.0, g.nel)
+    dfx = -c0 / (xm + 0.1) ** 2
+    gxv = np.array([xm.mean() - 0.3])
+    dgx = np.full(g.nel, 1.0 / g.nel)
+    lo, hi = mo.set_outer_movelimit(0.0, 1.0, 0.2, xm)
+    xn = mo.update(xm, dfx, gxv, [dgx], lo, hi)
+    xl, lo_l, hi_l = xm[e0:e1].copy(), np.empty(e1 - e0), np.empty(e1 - e0)
+    mg.SetOuterMovelimit(0.0, 1.0, 0.2, xl, lo_l, hi_l)
+    mg.Update(xl, dfx[e0:e1].copy(), gxv, [dgx[e0:e1].copy()], lo_l, hi_l)
+    assert np.abs(xl - xn[e0:e1]).max() <= 1e-9, ("mma", it)
+    xm = xn
+for obj in (mg, flt, phys):
+    obj.close()
+ctx.close()
+dist.barrier()
+if rank == 0:
+    print("MP_PARITY_OK")
+dist.destroy_process_group()

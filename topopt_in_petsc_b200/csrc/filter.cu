@@ -340,7 +340,6 @@ int tob_filter_increase_beta(double* beta, double beta_final, double gx, int itr
         if (beta[0] < 7) beta[0] = beta[0] + 1;
         else beta[0] = beta[0] * 1.2;
         if (beta[0] > beta_final) { beta[0] = beta_final; change = 0; }
-        printf("Beta has been increased to: %f\n", beta[0]);
     }
     if (changed) *changed = change;
     return 0;
