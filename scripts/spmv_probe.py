@@ -8,7 +8,7 @@ from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
 ap = argparse.ArgumentParser()
 ap.add_argument("--sizes", default="192x96x96,256x256x256")
 ap.add_argument("--reps", type=int, default=20)
-ap.add_argument("--kernels", default="1,2,3,4,5")
+ap.add_argument("--kernels", default="1,2,3,4,5,6,7,8")
 ap.add_argument("--micro", type=int, default=1)
 ap.add_argument("--dens", default="uniform")
 a = ap.parse_args()
@@ -22,7 +22,7 @@ if a.micro:
     out["copy_gbs_1GiB"] = ctx.microbench_copy(1 << 30)
     ctx.close()
     print(json.dumps(out), flush=True)
-names = {1: "naive_dense", 2: "zmarch_ty8", 3: "zmarch_ty16", 4: "zmarch_ty12_regs", 5: "zmarch_ty8_regs"}
+names = {1: "naive_dense", 2: "zmarch_ty8", 3: "zmarch_ty16", 4: "zmarch_ty12_regs", 5: "zmarch_ty8_regs", 6: "zmarch_ty8_regs_flags", 7: "zmarch_ty16_regs_flags", 8: "zmarch_ty12_regs_flags"}
 for sz in a.sizes.split(","):
     ex, ey, ez = [int(v) for v in sz.split("x")]
     ctx = Context(ex + 1, ey + 1, ez + 1)

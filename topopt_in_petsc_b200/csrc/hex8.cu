@@ -184,6 +184,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void lds2(double& a, double& b, uint32_t addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
@@ -203,7 +211,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
 // ---------------------------------------------------------------------------------------
 // z-march kernel
 // ---------------------------------------------------------------------------------------
-constexpr int ZM_STAGES = 4;
 
 struct ZmParams {
     int nxn, nyn, nzl;
@@ -225,7 +232,7 @@ struct ZmParams {
 // coordinate must be 16-byte aligned (measured: odd fp64 origins raise "illegal instruction"), so the
 // box starts at the even column bx*30-2 and thread tx reads column tx+1.
 constexpr int ZM_W = 34;
-template <int TY, bool SMEM_STATE = true>
+template <int TY, bool SMEM_STATE = true, bool FLAGS = false>
 struct ZmSmem {
     static constexpr int NT = 32 * TY;
     static constexpr int NC = ZM_W * TY;          // doubles per component tile
@@ -233,27 +240,37 @@ struct ZmSmem {
     static constexpr int E_BYTES = (NC * 8 + 127) / 128 * 128;
     static constexpr int TX_BYTES = 4 * NC * 8;                     // bytes the two TMA loads deliver per stage
     static constexpr int STAGE_BYTES = U_BYTES + E_BYTES;
-    static constexpr int XCH_BYTES = 2 * 6 * NT * 8;
+    static constexpr int XCH_DEPTH = FLAGS ? 4 : 2;               // exchange-buffer ring (y-neighbour hand-off)
+    static constexpr int XCH_BYTES = XCH_DEPTH * 6 * NT * 8;
     static constexpr int UP_BYTES = SMEM_STATE ? 24 * NT * 8 : 0;  // carried state when kept out of registers
-    static constexpr int KB_OFF = ZM_STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;  // 48 block constants
+    // TMA ring depth: with the delayed refill (the plane below is re-read for the output) the prefetch
+    // distance is STAGES-2 planes; the register-state variants have shared memory to spare for a deeper ring.
+    static constexpr int STAGES = SMEM_STATE ? 4 : 6;
+    static constexpr int KB_OFF = STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;  // 48 block constants
     static constexpr int BAR_OFF = KB_OFF + 48 * 8;
-    static constexpr int TOTAL = BAR_OFF + ZM_STAGES * 8 + 128;
+    static constexpr int FLAG_OFF = BAR_OFF + STAGES * 8 + 64;       // row sequence / completion counters
+    static constexpr int TOTAL = FLAG_OFF + 2 * 32 * 4 + 128;
 };
 
 // SMEM_STATE: the 24 doubles carried from one z-step to the next (lower-face modes + upper-face
 // contributions) live in shared memory (lets two 256-thread CTAs share an SM at 128 registers) or in
 // registers (one CTA per SM with a larger register budget; less shared-memory traffic).
-template <int TY, int EPI, bool SMEM_STATE>
+// FLAGS: instead of one __syncthreads per z-step, warp row ty waits only for row ty-1 (per-row sequence
+// counters in shared memory, st.release / ld.acquire); ring slots are recycled when every row's completion
+// counter has passed them.  ncu on the barrier version: 1.5 of ~4 resident warps per scheduler sat at the barrier.
+template <int TY, int EPI, bool SMEM_STATE, bool FLAGS>
 __global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
 k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
               const __grid_constant__ Hex8Blocks KB, const __grid_constant__ ZmParams P) {
-    using L = ZmSmem<TY, SMEM_STATE>;
+    using L = ZmSmem<TY, SMEM_STATE, FLAGS>;
     constexpr int NT = L::NT;
     constexpr int NC = L::NC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    int* rowseq = reinterpret_cast<int*>(smem_raw + L::FLAG_OFF);  // [ty] = steps whose y-hand-off data is published
+    int* rowdone = rowseq + 32;                                    // [ty] = steps completely finished
     __shared__ double red[32];
-    double* xch = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES);
-    double* ups = reinterpret_cast<double*>(smem_raw + ZM_STAGES * L::STAGE_BYTES + L::XCH_BYTES) + (threadIdx.x);
+    double* xch = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES);
+    double* ups = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES + L::XCH_BYTES) + (threadIdx.x);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
     // symmetric 3x3 blocks, 6 unique entries each (b00 b01 b02 b11 b12 b22), read back with broadcast
     // ld.shared.v2.f64: keeping 72 constants in uniform registers made the loop issue-bound.
@@ -278,15 +295,16 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             const int r = k < 3 ? 0 : (k < 5 ? 1 : 2), cc = k < 3 ? k : (k < 5 ? k - 2 : 2);
             kbs[tid] = KB.b[rho][3 * r + cc];
         }
+        if (tid < 64) rowseq[tid] = (tid >= 32 + TY - 1) ? 0x3fffffff : 0;  // the idle top row never blocks a refill
         if (tid == 0) {
-            for (int s = 0; s < ZM_STAGES; s++) mbar_init(&bars[s], 1);
+            for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncthreads();
 
         auto issue = [&](int pidx) {  // pidx = plane counter 0..nplanes-1, plane = pfirst + pidx
-            const int s = pidx % ZM_STAGES;
+            const int s = pidx % L::STAGES;
             unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const int p = pfirst + pidx;
             mbar_expect_tx(&bars[s], L::TX_BYTES);
@@ -298,8 +316,17 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         auto load_mask = [&](int p) -> unsigned {
             return (innode && p >= 0 && p < P.nzl) ? (unsigned)P.mask[(long long)p * P.mstride + (long long)j * P.pm + i] : 0u;
         };
+        int issued = 0;  // (thread 0) next plane counter to issue
         if (tid == 0)
-            for (int s = 0; s < ZM_STAGES && s < nplanes; s++) issue(s);
+            for (; issued < L::STAGES && issued < nplanes; issued++) issue(issued);
+        // FLAGS: plane q may overwrite ring slot q % STAGES once every row finished step q - STAGES (the step that
+        // re-reads plane q - STAGES for its output), i.e. all rowdone >= q - STAGES + 1.
+        auto min_done = [&]() {
+            int m = 0x3fffffff;
+#pragma unroll
+            for (int r = 0; r < TY - 1; r++) m = min(m, ld_acquire(&rowdone[r]));
+            return m;
+        };
 
         double* fps = ups + 12 * NT;  // face modes of the lower plane of the current element
         double fpr[12], upr[12];      // register copies of the carried state (SMEM_STATE == false)
@@ -348,13 +375,21 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         const int nsteps = z1 - pfirst;
         for (int t = 0; t < nsteps; t++) {
             const int pidx = t + 1;
-            const int s = pidx % ZM_STAGES;
+            const int s = pidx % L::STAGES;
             const unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const unsigned mnew = load_mask(pfirst + pidx);  // consumed one step later
-            mbar_wait(&bars[s], (pidx / ZM_STAGES) & 1);
+            if (FLAGS) {
+                if (ty == TY - 1) continue;  // idle row: nothing to compute, nothing to hand over
+                if (tid == 0)
+                    while (issued <= pidx) {  // my own next plane is not in flight yet: wait for the slowest row
+                        while (min_done() < issued - L::STAGES + 1) {}
+                        issue(issued++);
+                    }
+            }
+            mbar_wait(&bars[s], (pidx / L::STAGES) & 1);
 
             double ex0[3][2];  // edge (row j) contributions of my face
-            double* xw = xch + (t & 1) * 6 * NT;
+            double* xw = xch + (t % L::XCH_DEPTH) * 6 * NT;
             if (compute) {
                 double fnew[3][4];
                 face_modes(st, fnew);
@@ -413,6 +448,8 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         else upr[4 * c + f] = yh[c][f] - yh[c][4 + f];
                     }
                 // Y' stage: row j part stays, row j+1 part goes to the thread above
+                if (FLAGS && ty + 1 <= TY - 2 && t >= L::XCH_DEPTH)  // the reader must be done with this slot's old data
+                    while (ld_acquire(&rowdone[ty + 1]) < t - L::XCH_DEPTH + 1) {}
 #pragma unroll
                 for (int c = 0; c < 3; c++)
 #pragma unroll
@@ -424,9 +461,15 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 #pragma unroll
                 for (int c = 0; c < 3; c++) { ex0[c][0] = 0.0; ex0[c][1] = 0.0; }
             }
-            __syncthreads();
-            // the ring slot of plane pidx-2 is free now (plane pidx-1 is still read below for the output)
-            if (tid == 0 && pidx >= 2 && pidx - 2 + ZM_STAGES < nplanes) issue(pidx - 2 + ZM_STAGES);
+            if (FLAGS) {
+                __syncwarp();
+                if (tx == 0) st_release(&rowseq[ty], t + 1);
+                if (ty >= 1) while (ld_acquire(&rowseq[ty - 1]) < t + 1) {}
+            } else {
+                __syncthreads();
+                // the ring slot of plane pidx-2 is free now (plane pidx-1 is still read below for the output)
+                if (tid == 0 && pidx >= 2 && pidx - 2 + L::STAGES < nplanes) issue(pidx - 2 + L::STAGES);
+            }
 
             // edge totals, X' stage, node totals
             double v[3], vr[3];
@@ -445,7 +488,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 
             const int e = pfirst + t;  // node plane completed by this step
             if (outthr && e >= z0) {
-                const double* sl = reinterpret_cast<const double*>(smem_raw + (t % ZM_STAGES) * L::STAGE_BYTES);
+                const double* sl = reinterpret_cast<const double*>(smem_raw + (t % L::STAGES) * L::STAGE_BYTES);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const long long idx = e * P.pstride + c * P.nstride + (long long)j * P.px + i;
@@ -470,6 +513,12 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 }
             }
             mown = mnew;
+            if (FLAGS) {
+                __syncwarp();
+                if (tx == 0) st_release(&rowdone[ty], t + 1);
+                if (tid == 0)  // opportunistic refill of every ring slot that all rows have left
+                    while (issued < nplanes && min_done() >= issued - L::STAGES + 1) issue(issued++);
+            }
         }
     }
     if (EPI == EPI_DOT || EPI == EPI_RESID) {
@@ -495,9 +544,9 @@ static int encode_map(tob_ctx_impl* c, CUtensorMap* tm, CUtensorMapDataType dt, 
     return 0;
 }
 
-template <int TY, int EPI, bool SMEM_STATE>
+template <int TY, int EPI, bool SMEM_STATE, bool FLAGS>
 static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
-    using L = ZmSmem<TY, SMEM_STATE>;
+    using L = ZmSmem<TY, SMEM_STATE, FLAGS>;
     CUtensorMap tmU, tmE;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, 3, (cuuint64_t)g.nzl()};
@@ -537,7 +586,7 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
     if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
-    auto kern = k_hex8_zmarch<TY, EPI, SMEM_STATE>;
+    auto kern = k_hex8_zmarch<TY, EPI, SMEM_STATE, FLAGS>;
     static bool attr_set = false;
     if (!attr_set) {
         TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -550,13 +599,13 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     return 0;
 }
 
-template <int TY, bool SMEM_STATE>
+template <int TY, bool SMEM_STATE, bool FLAGS>
 static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     switch (a.epi) {
-        case EPI_Y: return launch_zm<TY, EPI_Y, SMEM_STATE>(c, g, op, a, nparts);
-        case EPI_DOT: return launch_zm<TY, EPI_DOT, SMEM_STATE>(c, g, op, a, nparts);
-        case EPI_RESID: return launch_zm<TY, EPI_RESID, SMEM_STATE>(c, g, op, a, nparts);
-        default: return launch_zm<TY, EPI_CHEB, SMEM_STATE>(c, g, op, a, nparts);
+        case EPI_Y: return launch_zm<TY, EPI_Y, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
+        case EPI_DOT: return launch_zm<TY, EPI_DOT, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
+        case EPI_RESID: return launch_zm<TY, EPI_RESID, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
+        default: return launch_zm<TY, EPI_CHEB, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
     }
 }
 
@@ -574,10 +623,13 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
         TOB_KERNEL_CHECK();
         return 0;
     }
-    if (kernel == SPMV_ZM16) return dispatch_zm<16, true>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM12) return dispatch_zm<12, false>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM8R) return dispatch_zm<8, false>(c, g, op, a, nparts);
-    return dispatch_zm<8, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16) return dispatch_zm<16, true, false>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM12) return dispatch_zm<12, false, false>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM8R) return dispatch_zm<8, false, false>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM8RF) return dispatch_zm<8, false, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16RF) return dispatch_zm<16, false, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM12RF) return dispatch_zm<12, false, true>(c, g, op, a, nparts);
+    return dispatch_zm<8, true, false>(c, g, op, a, nparts);
 }
 
 // ---------------------------------------------------------------------------------------
