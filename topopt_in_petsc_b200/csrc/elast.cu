@@ -205,6 +205,10 @@ int elast_set_bc_load(tob_elast_impl* h, const unsigned char* fixed, const doubl
     TOB_CHECK(read_scalars(c, S_BB, 1, &bb));
     h->bnorm = sqrt(bb);
     if (h->have_density) TOB_CHECK(hex8_diag_inv(c, g, h->op, h->E_st, h->mask, h->DINV, true));
+    if (h->mg) {
+        TOB_CHECK(gmg_refresh_masks(h));
+        if (h->have_density) TOB_CHECK(gmg_update(h));
+    }
     return 0;
 }
 

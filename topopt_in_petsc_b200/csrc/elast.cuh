@@ -45,6 +45,7 @@ int mask_to_free(tob_ctx_impl* c, const LevelGrid& g, const unsigned char* mask,
 // geometric multigrid preconditioner (gmg.cu)
 int gmg_setup(tob_elast_impl* h);
 int gmg_update(tob_elast_impl* h);   // refresh coarse operators after a density change
+int gmg_refresh_masks(tob_elast_impl* h);  // inject the Dirichlet mask to the coarse levels
 int gmg_vcycle(tob_elast_impl* h, const double* r, double* z);
 void gmg_destroy(tob_elast_impl* h);
 

@@ -1,9 +1,381 @@
-// gmg.cu -- geometric multigrid V-cycle preconditioner (placeholder until the hierarchy lands)
+// gmg.cu -- geometric multigrid V-cycle preconditioner for the matrix-free PCG.
+// Replaces PCMG + DMCoarsenHierarchy + DMCreateInterpolation + Galerkin PtAP + GMRES/SOR smoothers
+// (LinearElasticity.cc:656-746).  B200 design:
+//   * the hierarchy is the structured grid coarsened by 2 (same z-slab boundaries on every level when the
+//     element layers per rank are divisible by 2^(nlvls-1)), each level is a LevelGrid, so the SAME
+//     TMA z-march hex8 kernel applies the operator on every level;
+//   * coarse operators are re-discretised with the 8-child average of the SIMP modulus (no assembly, no PtAP;
+//     the refresh after a density change is one tiny kernel per level);
+//   * smoother = Chebyshev polynomial in D^-1 A, each step ONE launch: the SpMV epilogue EPI_CHEB forms the
+//     residual, the 3-term recurrence and the new iterate.  The eigenvalue bound needs no power iteration:
+//     lambda_max(D^-1 A) <= lambda_max(diag(KE)^-1 KE) for ANY modulus field (element-wise Rayleigh bound);
+//   * transfers are trilinear (Q1) prolongation per component and its transpose, as the reference's DMDA
+//     interpolation; Dirichlet dofs are injected to the coarse levels;
+//   * coarsest level: a fixed number of Jacobi-PCG iterations driven entirely by device scalars (no host sync).
 #include "elast.cuh"
+#include "vecops.cuh"
+
 namespace tob {
-struct GmgHierarchy { int dummy; };
-int gmg_setup(tob_elast_impl* h) { (void)h; TOB_FAIL("multigrid preconditioner (pc=1) not built yet"); }
-int gmg_update(tob_elast_impl* h) { (void)h; return 0; }
-int gmg_vcycle(tob_elast_impl* h, const double* r, double* z) { (void)h; (void)r; (void)z; TOB_FAIL("multigrid preconditioner not built yet"); }
-void gmg_destroy(tob_elast_impl* h) { if (h->mg) { delete h->mg; h->mg = nullptr; } }
+
+struct GmgLevel {
+    LevelGrid g;
+    Hex8Operator op;
+    bool own_op = false;
+    double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *dinv = nullptr, *E = nullptr;
+    unsigned char* mask = nullptr;
+    bool own_E = false;
+};
+
+struct GmgHierarchy {
+    std::vector<GmgLevel> lv;
+    double lam_max = 2.0;   // bound on lambda_max(D^-1 A)
+    double lam_ratio = 8.0; // Chebyshev targets [lam_max/ratio, lam_max]
+    // coarsest-level PCG vectors
+    double *cp = nullptr, *cq = nullptr;
+};
+
+enum { G_S_PQ = 20, G_S_PAIR_A = 22, G_S_PAIR_B = 24 };
+
+// ---- kernels ------------------------------------------------------------------------------------
+// coarse modulus = mean of the 8 children (owned coarse layers; ghosts are exchanged afterwards)
+__global__ void k_coarsen_E(const double* __restrict__ Ef, double* __restrict__ Ec, int ncx, int ncy, int pef, int pec,
+                            long long esf, long long esc, int lf0, int lc0, int nlc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, l = blockIdx.z;
+    if (i >= ncx || l >= nlc) return;
+    double s = 0.0;
+    for (int dk = 0; dk < 2; dk++)
+        for (int dj = 0; dj < 2; dj++)
+            for (int di = 0; di < 2; di++) s += Ef[(lf0 + 2 * l + dk) * esf + (long long)(2 * j + dj) * pef + 2 * i + di];
+    Ec[(lc0 + l) * esc + (long long)j * pec + i] = 0.125 * s;
+}
+
+__global__ void k_inject_mask(const unsigned char* __restrict__ mf, unsigned char* __restrict__ mc, int ncx, int ncy, int pmf,
+                              int pmc, long long msf, long long msc, int zf0, int zc0, int nzc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= ncx || k >= nzc) return;
+    mc[(zc0 + k) * msc + (long long)j * pmc + i] = mf[(zf0 + 2 * k) * msf + (long long)(2 * j) * pmf + 2 * i];
+}
+
+// rc = P^T rf on owned coarse planes (fine ghost planes must be current); clamped coarse dofs get 0
+__global__ void __launch_bounds__(128)
+k_restrict(const double* __restrict__ rf, double* __restrict__ rc, const unsigned char* __restrict__ mc, int nfx, int nfy,
+           int nfzl, int ncx, int ncy, int pxf, int pxc, int pmc, long long nsf, long long psf, long long nsc, long long psc,
+           long long msc, int zc0, int nzc, int gc0, int gf0) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y, K = blockIdx.z;
+    if (I >= ncx || K >= nzc) return;
+    const int kc = zc0 + K;               // local coarse plane
+    const int kf = 2 * (kc + gc0) - gf0;  // local fine plane coincident with it
+    double acc[3] = {0, 0, 0};
+    for (int dk = -1; dk <= 1; dk++) {
+        const int z = kf + dk;
+        if (z < 0 || z >= nfzl) continue;
+        for (int dj = -1; dj <= 1; dj++) {
+            const int y = 2 * J + dj;
+            if (y < 0 || y >= nfy) continue;
+            for (int di = -1; di <= 1; di++) {
+                const int x = 2 * I + di;
+                if (x < 0 || x >= nfx) continue;
+                const double w = (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0);
+                const long long o = z * psf + (long long)y * pxf + x;
+                acc[0] = fma(w, rf[o], acc[0]);
+                acc[1] = fma(w, rf[o + nsf], acc[1]);
+                acc[2] = fma(w, rf[o + 2 * nsf], acc[2]);
+            }
+        }
+    }
+    const unsigned char m = mc[kc * msc + (long long)J * pmc + I];
+    for (int c = 0; c < 3; c++) rc[kc * psc + c * nsc + (long long)J * pxc + I] = (m & (1 << c)) ? 0.0 : acc[c];
+}
+
+// xf += P xc on owned fine planes (coarse ghost planes must be current); clamped fine dofs stay untouched
+__global__ void __launch_bounds__(128)
+k_prolong_add(double* __restrict__ xf, const double* __restrict__ xc, const unsigned char* __restrict__ mf, int nfx, int nfy,
+              int pxf, int pxc, int pmf, long long nsf, long long psf, long long nsc, long long psc, long long msf, int zf0,
+              int nzf, int gf0, int gc0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= nfx || k >= nzf) return;
+    const int kf = zf0 + k;
+    const int kg = kf + gf0;  // global fine plane
+    const int I0 = i >> 1, J0 = j >> 1, K0 = (kg >> 1) - gc0;
+    const int ni = 1 + (i & 1), nj = 1 + (j & 1), nk = 1 + (kg & 1);
+    const double w = 1.0 / (ni * nj * nk);
+    double acc[3] = {0, 0, 0};
+    for (int a = 0; a < nk; a++)
+        for (int b = 0; b < nj; b++)
+            for (int c = 0; c < ni; c++) {
+                const long long o = (K0 + a) * psc + (long long)(J0 + b) * pxc + I0 + c;
+                acc[0] += xc[o];
+                acc[1] += xc[o + nsc];
+                acc[2] += xc[o + 2 * nsc];
+            }
+    const unsigned char m = mf[kf * msf + (long long)j * pmf + i];
+    for (int c = 0; c < 3; c++)
+        if (!(m & (1 << c))) xf[kf * psf + c * nsf + (long long)j * pxf + i] += w * acc[c];
+}
+
+// first Chebyshev step from a zero iterate: d = s1 * dinv * b ; x = d
+__global__ void __launch_bounds__(kFlatThreads) k_cheb_first(double* __restrict__ x, double* __restrict__ d, const double* __restrict__ b,
+                                                             const double* __restrict__ dinv, double s1, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = s1 * dinv[i] * b[i];
+        d[i] = v;
+        x[i] = v;
+    }
+}
+
+// ---- helpers ----------------------------------------------------------------------------------------
+static int galloc(tob_ctx_impl* c, double** p, long long n) {
+    TOB_CUDA(cudaMalloc(p, sizeof(double) * n));
+    TOB_CUDA(cudaMemsetAsync(*p, 0, sizeof(double) * n, c->stream));
+    return 0;
+}
+
+static double element_rayleigh_bound(const double* KE) {
+    // lambda_max(diag(KE)^-1 KE) by power iteration on the 24x24 matrix (host, once)
+    double v[24], w[24];
+    for (int i = 0; i < 24; i++) v[i] = 1.0 + 0.37 * ((i * 7) % 5) - 0.11 * i;
+    double lam = 1.0;
+    for (int it = 0; it < 500; it++) {
+        double nrm = 0;
+        for (int i = 0; i < 24; i++) {
+            double s = 0;
+            for (int j = 0; j < 24; j++) s += KE[i * 24 + j] * v[j];
+            w[i] = s / KE[i * 24 + i];
+            nrm += w[i] * w[i];
+        }
+        nrm = sqrt(nrm);
+        lam = nrm;
+        for (int i = 0; i < 24; i++) v[i] = w[i] / nrm;
+    }
+    return lam;
+}
+
+static int level_apply(tob_elast_impl* h, GmgLevel& L, const SpmvArgs& a0, int* nparts) {
+    SpmvArgs a = a0;
+    a.E = L.E; a.mask = L.mask; a.mask_in = false;
+    a.kernel = h->opts.spmv_kernel;
+    if (&L == &h->mg->lv[0]) h->stats.spmv_calls++;
+    return hex8_spmv(h->c, L.g, L.op, a, nparts);
+}
+
+// k Chebyshev-Jacobi steps on A x = b.  zero_init: x is taken as 0 (saves the first SpMV).
+// The iterate ends in L.x (ping-pong with L.x2).
+static int cheb_smooth(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    const double lmax = 1.02 * mg->lam_max, lmin = mg->lam_max / mg->lam_ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    double* xin = L.x;
+    double* xout = L.x2;
+    for (int s = 0; s < k; s++) {
+        double s0, s1;
+        if (s == 0) { s0 = 0.0; s1 = 1.0 / theta; }
+        else {
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            s0 = rho_new * rho;
+            s1 = 2.0 * rho_new / delta;
+            rho = rho_new;
+        }
+        if (s == 0 && zero_init) {
+            const LevelGrid& g = L.g;
+            k_cheb_first<<<flat_grid(c, g.own_len), kFlatThreads, 0, c->stream>>>(xin + g.own_off, L.d + g.own_off, L.b + g.own_off,
+                                                                                L.dinv + g.own_off, s1, g.own_len);
+            c->launches++;
+            TOB_KERNEL_CHECK();
+            continue;  // iterate stays in xin
+        }
+        TOB_CHECK(halo_nodes(c, L.g, xin));
+        SpmvArgs a;
+        a.u = xin; a.y = xout; a.epi = EPI_CHEB; a.a0 = L.b; a.a1 = L.dinv; a.o1 = L.d; a.s0 = s0; a.s1 = s1;
+        TOB_CHECK(level_apply(h, L, a, nullptr));
+        double* t = xin; xin = xout; xout = t;
+    }
+    if (xin != L.x) { double* t = L.x; L.x = L.x2; L.x2 = t; }
+    return 0;
+}
+
+// fixed number of Jacobi-PCG iterations on the coarsest level, x0 = 0, no host synchronisation
+static int coarse_solve(tob_elast_impl* h, GmgLevel& L, int its) {
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    const LevelGrid& g = L.g;
+    TOB_CHECK(vec_zero(c, L.x, g.nvec));
+    TOB_CHECK(vec_copy(c, L.r, L.b, g.nvec));
+    int cur = G_S_PAIR_A, nxt = G_S_PAIR_B, np = 0;
+    // slots 0/1 hold the constants 0 and 1 (elast.cu): alpha = 0 pass produces rr, rz
+    TOB_CHECK(pcg_update_xr(c, g, L.x, L.r, L.r, L.r, L.dinv, 0, 1, cur));
+    TOB_CHECK(pcg_update_p(c, g, mg->cp, L.r, L.dinv, 0, 1, 1));
+    for (int it = 0; it < its; it++) {
+        TOB_CHECK(halo_nodes(c, g, mg->cp));
+        SpmvArgs a;
+        a.u = mg->cp; a.y = mg->cq; a.epi = EPI_DOT;
+        TOB_CHECK(level_apply(h, L, a, &np));
+        TOB_CHECK(finalize_sum(c, np, 1, G_S_PQ, true));
+        TOB_CHECK(pcg_update_xr(c, g, L.x, L.r, mg->cp, mg->cq, L.dinv, cur + 1, G_S_PQ, nxt));
+        TOB_CHECK(pcg_update_p(c, g, mg->cp, L.r, L.dinv, nxt + 1, cur + 1, 0));
+        int t = cur; cur = nxt; nxt = t;
+    }
+    return 0;
+}
+
+static int vcycle(tob_elast_impl* h, int l) {
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    GmgLevel& L = mg->lv[l];
+    const int nl = (int)mg->lv.size();
+    if (l == nl - 1) return coarse_solve(h, L, h->opts.coarse_its);
+    const int k = h->opts.cheb_degree;
+    TOB_CHECK(cheb_smooth(h, L, k, true));
+    // residual r = b - A x
+    TOB_CHECK(halo_nodes(c, L.g, L.x));
+    SpmvArgs a;
+    a.u = L.x; a.y = L.r; a.epi = EPI_RESID; a.a0 = L.b;
+    TOB_CHECK(level_apply(h, L, a, nullptr));
+    // restrict
+    GmgLevel& C = mg->lv[l + 1];
+    TOB_CHECK(halo_nodes(c, L.g, L.r));
+    {
+        const LevelGrid &f = L.g, &g = C.g;
+        dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());
+        k_restrict<<<grid, 128, 0, c->stream>>>(L.r, C.b, C.mask, f.nxn, f.nyn, f.nzl(), g.nxn, g.nyn, f.px, g.px, g.pm, f.nstride,
+                                                f.pstride, g.nstride, g.pstride, g.mstride, g.zl_own0(), g.zl_own1() - g.zl_own0(),
+                                                g.gn0, f.gn0);
+        c->launches++;
+        TOB_KERNEL_CHECK();
+    }
+    TOB_CHECK(vcycle(h, l + 1));
+    // prolong and correct
+    TOB_CHECK(halo_nodes(c, C.g, C.x));
+    {
+        const LevelGrid &f = L.g, &g = C.g;
+        dim3 grid(div_up(f.nxn, 128), f.nyn, f.zl_own1() - f.zl_own0());
+        k_prolong_add<<<grid, 128, 0, c->stream>>>(L.x, C.x, L.mask, f.nxn, f.nyn, f.px, g.px, f.pm, f.nstride, f.pstride, g.nstride,
+                                                   g.pstride, f.mstride, f.zl_own0(), f.zl_own1() - f.zl_own0(), f.gn0, g.gn0);
+        c->launches++;
+        TOB_KERNEL_CHECK();
+    }
+    return cheb_smooth(h, L, k, false);
+}
+
+int gmg_vcycle(tob_elast_impl* h, const double* r, double* z) {
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    if (!mg) TOB_FAIL("multigrid hierarchy not set up");
+    GmgLevel& L0 = mg->lv[0];
+    TOB_CHECK(vec_copy(c, L0.b, r, L0.g.nvec));
+    TOB_CHECK(vcycle(h, 0));
+    return vec_copy(c, z, L0.x, L0.g.nvec);
+}
+
+int gmg_update(tob_elast_impl* h) {
+    // refresh coarse moduli and diagonals after a density change (replaces KSPSetOperators/KSPSetUp + PtAP,
+    // LinearElasticity.cc:198-200)
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    if (!mg) return 0;
+    mg->lv[0].E = h->E_st;
+    mg->lv[0].dinv = h->DINV;
+    mg->lv[0].mask = h->mask;
+    for (size_t l = 1; l < mg->lv.size(); l++) {
+        GmgLevel &F = mg->lv[l - 1], &C = mg->lv[l];
+        const LevelGrid &f = F.g, &g = C.g;
+        const int nlc = g.ke1 - g.ke0;
+        dim3 grid(div_up(g.nex, 128), g.ney, nlc);
+        k_coarsen_E<<<grid, 128, 0, c->stream>>>(F.E, C.E, g.nex, g.ney, f.pe, g.pe, f.estride, g.estride, f.ke0 - f.ge0,
+                                                 g.ke0 - g.ge0, nlc);
+        c->launches++;
+        TOB_KERNEL_CHECK();
+        const int own0 = g.ke0 - g.ge0, own1 = g.ke1 - g.ge0;
+        TOB_CHECK(halo_elems(c, C.E, g.estride, own0, own1, 0, g.nzle() - own1, c->desc.rank > 0 ? 1 : 0, 0));
+        TOB_CHECK(hex8_diag_inv(c, g, C.op, C.E, C.mask, C.dinv, true));
+    }
+    return 0;
+}
+
+int gmg_setup(tob_elast_impl* h) {
+    tob_ctx_impl* c = h->c;
+    if (h->mg) return 0;
+    const LevelGrid& g0 = *h->g;
+    const int nl = h->opts.nlvls;
+    if (nl < 2) TOB_FAIL("multigrid needs nlvls >= 2");
+    const int div = 1 << (nl - 1);
+    if (g0.nex % div || g0.ney % div || g0.nez % div) TOB_FAIL("MESH DIMENSION NOT COMPATIBLE WITH NUMBER OF MULTIGRID LEVELS (TopOpt.cc:182-201)");
+    if ((g0.ke0 % div) || (g0.ke1 % div)) TOB_FAIL("z-slab boundaries must be multiples of 2^(nlvls-1) element layers");
+    auto* mg = new GmgHierarchy();
+    mg->lv.resize(nl);
+    mg->lam_max = element_rayleigh_bound(h->op.KE);
+    GmgLevel& L0 = mg->lv[0];
+    L0.g = g0;
+    L0.op = h->op;
+    L0.E = h->E_st; L0.dinv = h->DINV; L0.mask = h->mask;
+    for (int l = 0; l < nl; l++) {
+        GmgLevel& L = mg->lv[l];
+        if (l > 0) {
+            const LevelGrid& f = mg->lv[l - 1].g;
+            const int rank = c->desc.rank;
+            const int ke0 = f.ke0 / 2, ke1 = f.ke1 / 2;
+            const int kn0 = rank == 0 ? 0 : ke0 + 1, kn1 = ke1 + 1;
+            make_level_grid(L.g, f.nex / 2 + 1, f.ney / 2 + 1, f.nez / 2 + 1, 2 * f.dx, 2 * f.dy, 2 * f.dz, rank, c->desc.nranks, kn0, kn1);
+            TOB_CHECK(hex8_build_operator(L.g.dx, L.g.dy, L.g.dz, h->nu, L.op));
+            L.own_op = true;
+            TOB_CHECK(galloc(c, &L.E, L.g.evec));
+            TOB_CHECK(galloc(c, &L.dinv, L.g.nvec));
+            TOB_CUDA(cudaMalloc(&L.mask, (size_t)L.g.mstride * L.g.nzl()));
+            TOB_CUDA(cudaMemsetAsync(L.mask, 0, (size_t)L.g.mstride * L.g.nzl(), c->stream));
+            L.own_E = true;
+        }
+        double** vs[] = {&L.x, &L.x2, &L.b, &L.r, &L.d};
+        for (auto v : vs) TOB_CHECK(galloc(c, v, L.g.nvec));
+    }
+    TOB_CHECK(galloc(c, &mg->cp, mg->lv[nl - 1].g.nvec));
+    TOB_CHECK(galloc(c, &mg->cq, mg->lv[nl - 1].g.nvec));
+    h->mg = mg;
+    TOB_CHECK(gmg_refresh_masks(h));
+    return 0;
+}
+
+int gmg_refresh_masks(tob_elast_impl* h) {
+    // Dirichlet dofs are injected level by level (all stored planes, ghosts included: the coarse plane
+    // coincident with a fine ghost plane is itself a stored coarse plane)
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    if (!mg) return 0;
+    mg->lv[0].mask = h->mask;
+    for (size_t l = 1; l < mg->lv.size(); l++) {
+        GmgLevel &F = mg->lv[l - 1], &C = mg->lv[l];
+        const LevelGrid &f = F.g, &g = C.g;
+        // local coarse plane kc <-> global 2*(kc+gc0) -> local fine 2*(kc+gc0)-gf0 ; handle via offset arithmetic
+        for (int kc = 0; kc < g.nzl(); kc++) {
+            const int kf = 2 * (kc + g.gn0) - f.gn0;
+            if (kf < 0 || kf >= f.nzl()) continue;
+            dim3 grid(div_up(g.nxn, 128), g.nyn, 1);
+            k_inject_mask<<<grid, 128, 0, c->stream>>>(F.mask, C.mask, g.nxn, g.nyn, f.pm, g.pm, f.mstride, g.mstride, kf, kc, 1);
+            c->launches++;
+        }
+        TOB_KERNEL_CHECK();
+    }
+    return 0;
+}
+
+void gmg_destroy(tob_elast_impl* h) {
+    GmgHierarchy* mg = h->mg;
+    if (!mg) return;
+    for (size_t l = 0; l < mg->lv.size(); l++) {
+        GmgLevel& L = mg->lv[l];
+        double* vs[] = {L.x, L.x2, L.b, L.r, L.d};
+        for (auto v : vs) cudaFree(v);
+        if (L.own_E) { cudaFree(L.E); cudaFree(L.dinv); cudaFree(L.mask); }
+        if (L.own_op) hex8_free_operator(L.op);
+    }
+    cudaFree(mg->cp);
+    cudaFree(mg->cq);
+    delete mg;
+    h->mg = nullptr;
+}
+
 }  // namespace tob
