@@ -150,3 +150,37 @@ def test_design_loop_vs_oracle(oracle):
     for o in (mma, flt, phys):
         o.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("shape,xc,rmin", [((17, 9, 9), (0, 2, 0, 1, 0, 1), 0.3), ((21, 13, 11), (0, 1.0, 0, 0.9, 0, 0.5), 0.21),
+                                           ((33, 17, 17), (0, 2, 0, 1, 0, 1), 0.08)])
+def test_pde_filter_vs_oracle(oracle, shape, xc, rmin):
+    """Helmholtz PDE filter (PDEFilter.cc:189-216): T^T K^-1 (vol T x), solved to rtol 1e-8 on both sides."""
+    from topopt_in_petsc_b200 import Context, Filter
+    rng = np.random.default_rng(2)
+    g = oracle.Grid(*shape, xc=xc)
+    po = oracle.PDEFilterOracle(g, rmin)
+    ctx = Context(*shape, xc=xc)
+    f = Filter(ctx, 2, rmin)
+    x = rng.uniform(0, 1, g.nel)
+    out = f.PDEApply(x)
+    ref = po.apply(x)
+    assert np.abs(out - ref).max() <= 1e-7
+    st = f.stats()
+    assert st.rel_residual <= 1e-8 and 0 < st.iterations < 2000
+    # preserves constants (rows of KF sum to vol/8) and is self-adjoint
+    assert np.abs(f.PDEApply(np.full(g.nel, 0.4)) - 0.4).max() <= 1e-7
+    y = rng.uniform(0, 1, g.nel)
+    assert abs(y @ out - x @ f.PDEApply(y)) <= 1e-6 * abs(y @ out)
+    # through the Filter surface: clamp to [0,1], projection, gradients
+    xt, xp = np.empty(g.nel), np.empty(g.nel)
+    f.FilterProject(x, xt, xp, True, 4.0, 0.3)
+    fo = oracle.FilterOracle(g, 2, rmin)
+    xt0, xp0 = fo.filter_project(x, True, 4.0, 0.3)
+    assert np.abs(xt - xt0).max() <= 1e-7 and np.abs(xp - xp0).max() <= 1e-6
+    df, dg = rng.uniform(-1, 0, g.nel), np.full(g.nel, 1.0 / g.nel)
+    df0, dg0 = fo.gradients(x, xt0, df, [dg], True, 4.0, 0.3)
+    f.Gradients(x, xt, df, 1, [dg], True, 4.0, 0.3)
+    assert np.abs(df - df0).max() <= 1e-6 * np.abs(df0).max() + 1e-9
+    assert np.abs(dg - dg0[0]).max() <= 1e-6 * np.abs(dg0[0]).max() + 1e-12
+    f.close(); ctx.close()

@@ -311,6 +311,7 @@ int tob_elast_destroy(tob_elast* h) {
 int tob_elast_set_opts(tob_elast* hh, const tob_solver_opts* o) {
     auto* h = reinterpret_cast<tob_elast_impl*>(hh);
     const bool need_mg = o->pc == 1 && !h->mg;
+    if (h->mg) gmg_drop_graph(h);
     h->opts = *o;
     if (need_mg) {
         TOB_CHECK(gmg_setup(h));

@@ -48,5 +48,6 @@ int gmg_update(tob_elast_impl* h);   // refresh coarse operators after a density
 int gmg_refresh_masks(tob_elast_impl* h);  // inject the Dirichlet mask to the coarse levels
 int gmg_vcycle(tob_elast_impl* h, const double* r, double* z);
 void gmg_destroy(tob_elast_impl* h);
+void gmg_drop_graph(tob_elast_impl* h);  // after a change of solver options
 
 }  // namespace tob

@@ -32,6 +32,12 @@ struct GmgHierarchy {
     double lam_ratio = 8.0; // Chebyshev targets [lam_max/ratio, lam_max]
     // coarsest-level PCG vectors
     double *cp = nullptr, *cq = nullptr;
+    // CUDA graph of one V-cycle
+    bool warm = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    const double* graph_r = nullptr;
+    double* graph_z = nullptr;
+    long long graph_launches = 0;
 };
 
 enum { G_S_PQ = 20, G_S_PAIR_A = 22, G_S_PAIR_B = 24 };
@@ -195,7 +201,8 @@ static int cheb_smooth(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
         TOB_CHECK(level_apply(h, L, a, nullptr));
         double* t = xin; xin = xout; xout = t;
     }
-    if (xin != L.x) { double* t = L.x; L.x = L.x2; L.x2 = t; }
+    // keep the buffer roles fixed (the V-cycle is replayed as a CUDA graph): copy back instead of swapping pointers
+    if (xin != L.x) TOB_CHECK(vec_copy(c, L.x + L.g.own_off, xin + L.g.own_off, L.g.own_len));
     return 0;
 }
 
@@ -267,9 +274,42 @@ int gmg_vcycle(tob_elast_impl* h, const double* r, double* z) {
     GmgHierarchy* mg = h->mg;
     if (!mg) TOB_FAIL("multigrid hierarchy not set up");
     GmgLevel& L0 = mg->lv[0];
-    TOB_CHECK(vec_copy(c, L0.b, r, L0.g.nvec));
-    TOB_CHECK(vcycle(h, 0));
-    return vec_copy(c, z, L0.x, L0.g.nvec);
+    // The V-cycle is a fixed sequence of ~100-250 small launches (coarse levels are launch-latency bound): the
+    // first call runs eagerly (sets kernel attributes), the second is captured into a CUDA graph, later calls
+    // replay it.  All operands (pointers, tensor maps, Chebyshev coefficients) are invariant across design
+    // iterations; the graph is dropped when solver options or buffers change.
+    if (mg->graph_exec && mg->graph_r == r && mg->graph_z == z) {
+        TOB_CUDA(cudaGraphLaunch(mg->graph_exec, c->stream));
+        c->launches += mg->graph_launches;
+        return 0;
+    }
+    const bool capture = mg->warm && h->opts.verbose != 2;
+    long long l0 = c->launches;
+    if (capture) TOB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = vec_copy(c, L0.b, r, L0.g.nvec);
+    if (!rc) rc = vcycle(h, 0);
+    if (!rc) rc = vec_copy(c, z, L0.x, L0.g.nvec);
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) TOB_FAIL(std::string("V-cycle graph capture failed: ") + cudaGetErrorString(e));
+        TOB_CUDA(cudaGraphInstantiate(&mg->graph_exec, graph, 0));
+        cudaGraphDestroy(graph);
+        mg->graph_r = r; mg->graph_z = z;
+        mg->graph_launches = c->launches - l0;
+        c->launches = l0;
+        TOB_CUDA(cudaGraphLaunch(mg->graph_exec, c->stream));
+        c->launches += mg->graph_launches;
+        return 0;
+    }
+    mg->warm = true;
+    return rc;
+}
+
+void gmg_drop_graph(tob_elast_impl* h) {
+    GmgHierarchy* mg = h->mg;
+    if (mg && mg->graph_exec) { cudaGraphExecDestroy(mg->graph_exec); mg->graph_exec = nullptr; }
 }
 
 int gmg_update(tob_elast_impl* h) {
@@ -365,6 +405,7 @@ int gmg_refresh_masks(tob_elast_impl* h) {
 void gmg_destroy(tob_elast_impl* h) {
     GmgHierarchy* mg = h->mg;
     if (!mg) return;
+    gmg_drop_graph(h);
     for (size_t l = 0; l < mg->lv.size(); l++) {
         GmgLevel& L = mg->lv[l];
         double* vs[] = {L.x, L.x2, L.b, L.r, L.d};
