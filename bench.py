@@ -84,11 +84,12 @@ class DesignLoop:
     """main.cc:48-105 over the C-ABI.  resident=True keeps every vector in HBM (DevVec); resident=False uses
     pinned host numpy buffers, so each C-ABI call stages host<->device inside the timed region."""
 
-    def __init__(self, ctx, resident, profile=True):
+    def __init__(self, ctx, resident, profile=True, pc=0, nlvls=4):
         from topopt_in_petsc_b200 import Filter, LinearElasticity, MMA, solver_opts
         self.ctx, self.resident = ctx, resident
         c = CFG
-        self.phys = LinearElasticity(ctx, nu=c["nu"], opts=solver_opts(pc=0, rtol=c["rtol"], maxits=100000, check_every=50))
+        self.phys = LinearElasticity(ctx, nu=c["nu"], opts=solver_opts(pc=pc, nlvls=nlvls, rtol=c["rtol"], coarse_its=60,
+                                                                       maxits=100000 if pc == 0 else 500, check_every=50))
         self.phys.SetProfile(profile)
         dx = 2.0 / c["nex"]
         self.flt = Filter(ctx, 1, c["rmin_cells"] * dx)
@@ -211,6 +212,19 @@ def run_ours(args):
     h2d, d2h = loop2.h2d // K, loop2.d2h // K
     loop2.close()
 
+    # ---- same job with the multigrid-preconditioned solver (not the BASELINE-named cfg2 solver; reported beside it) ----
+    nlv = 4
+    while nlv > 2 and (c["nez"] // world) % (1 << (nlv - 1)):
+        nlv -= 1
+    gmg = None
+    if (c["nez"] // world) % (1 << (nlv - 1)) == 0 and not args.no_gmg:
+        loop3 = DesignLoop(ctx, resident=True, pc=1, nlvls=nlv)
+        ms3, _, its3 = timed(loop3, K, W)
+        gmg = {"value": K / (ms3 * 1e-3), "unit": "design iterations/s (whole job)", "ms_per_step": ms3 / K, "nlvls": nlv,
+               "pcg_iterations_per_step": its3, "smoother": "Chebyshev-Jacobi degree 4", "coarse": "60 Jacobi-PCG iterations",
+               "final_fx": loop3.hist[-1]["fx"]}
+        loop3.close()
+
     if rank == 0:
         peak, kind = peaks()
         nel, ndof = ctx.nel, ctx.ndof
@@ -240,6 +254,7 @@ def run_ours(args):
                          "avg_launch_us": (spmv_s / spmv_n * 1e6) if spmv_n else None,
                          "share_of_step": (spmv_s / (ms * 1e-3)) if spmv_s else None},
             "history": [{k: (round(v, 9) if isinstance(v, float) else v) for k, v in h.items()} for h in hist[W:]],
+            "gmg_solver": gmg,
         }
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_sample(steps=1, warmup=0, its_full=int(np.mean(its)) if its else None)
@@ -311,6 +326,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gmg", action="store_true", help="skip the extra multigrid-solver leg")
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3  # timing rule: at least 3 warm-up steps
