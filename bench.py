@@ -199,25 +199,26 @@ def run_ours(args):
         return float(ms.item()), clocks, loop.pcg_its[nwarm:]
 
     K, W = args.steps, args.warmup
+    nlv = 4
+    while nlv > 2 and (c["nez"] // world) % (1 << (nlv - 1)):
+        nlv -= 1
+    main_pc = 1 if args.solver == "gmg" else 0
     # ---- device-resident arm -----------------------------------------------------------------
-    loop = DesignLoop(ctx, resident=True)
+    loop = DesignLoop(ctx, resident=True, pc=main_pc, nlvls=nlv)
     ms, clocks, its = timed(loop, K, W, ClockSampler(local))
     launches = ctx.launch_count()
     spmv_s, spmv_n = loop.spmv_s, loop.spmv_n
     hist = loop.hist
     loop.close()
     # ---- end-to-end arm: host (pinned) buffers through the same C-ABI calls ---------------------------
-    loop2 = DesignLoop(ctx, resident=False)
+    loop2 = DesignLoop(ctx, resident=False, pc=main_pc, nlvls=nlv)
     ms2, _, _ = timed(loop2, K, W)
     h2d, d2h = loop2.h2d // K, loop2.d2h // K
     loop2.close()
 
     # ---- same job with the multigrid-preconditioned solver (not the BASELINE-named cfg2 solver; reported beside it) ----
-    nlv = 4
-    while nlv > 2 and (c["nez"] // world) % (1 << (nlv - 1)):
-        nlv -= 1
     gmg = None
-    if (c["nez"] // world) % (1 << (nlv - 1)) == 0 and not args.no_gmg:
+    if (c["nez"] // world) % (1 << (nlv - 1)) == 0 and not args.no_gmg and main_pc == 0:
         loop3 = DesignLoop(ctx, resident=True, pc=1, nlvls=nlv)
         ms3, _, its3 = timed(loop3, K, W)
         gmg = {"value": K / (ms3 * 1e-3), "unit": "design iterations/s (whole job)", "ms_per_step": ms3 / K, "nlvls": nlv,
@@ -327,7 +328,15 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gmg", action="store_true", help="skip the extra multigrid-solver leg")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 = BASELINE configs[1] 192x96x96 (default, the headline); cfg3 = configs[2] 384x192x192 (scaling studies)")
+    ap.add_argument("--solver", default="jacobi", choices=["jacobi", "gmg"], help="state-solve preconditioner of the main arm")
     a = ap.parse_args()
+    os.environ["NCCL_DEBUG"] = os.environ.get("TOB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    if a.workload == "cfg3":
+        CFG.update(nex=384, ney=192, nez=192)
+        WORKLOAD = "cantilever 384x192x192, matrix-free PCG + geometric multigrid V-cycle, density filter rmin=3 cells, MMA m=1"
+        a.solver = "gmg"
     if a.warmup < 3 and a.impl == "ours":
         a.warmup = 3  # timing rule: at least 3 warm-up steps
     if a.impl == "reference":

@@ -87,7 +87,17 @@ struct DevBuf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// NVLink peer-memory transport (comm.cu): one IPC-exported arena per rank
+constexpr int kMaxRanks = 16;
+struct PeerComm {
+    bool enabled = false;
+    unsigned char* arena = nullptr;          // my arena
+    unsigned char* peer[kMaxRanks] = {};     // every rank's arena mapped into this process (peer[rank] == arena)
+    size_t bytes = 0, plane_bytes = 0;
+};
+
 struct tob_ctx_impl {
+    PeerComm peer;
     tob_grid_desc desc{};
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -131,6 +141,9 @@ int halo_nodes(tob_ctx_impl* c, const LevelGrid& g, double* v);
 // fills ghost element layers of a stored element field from the z-neighbours (see comm.cu)
 int halo_elems(tob_ctx_impl* c, double* v, long long layer_stride, int own0, int own1, int recv_lo, int recv_hi,
                int send_down, int send_up);
+int peer_setup(tob_ctx_impl* c, size_t plane_bytes);
+void peer_teardown(tob_ctx_impl* c);
+int finalize_allreduce(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, int op);  // -1 = not available
 int allreduce_sum(tob_ctx_impl* c, double* d_vals, int n);
 int allreduce_max(tob_ctx_impl* c, double* d_vals, int n);
 

@@ -147,6 +147,7 @@ int tob_ctx_create(const tob_grid_desc* d, tob_ctx** out) {
         ncclUniqueId id;
         memcpy(&id, d->nccl_id, sizeof id);
         TOB_NCCL(ncclCommInitRank(&c->comm, d->nranks, id, d->rank));
+        TOB_CHECK(peer_setup(c, sizeof(double) * (size_t)c->g0.pstride));
     }
     TOB_CUDA(cudaStreamSynchronize(c->stream));
     *out = reinterpret_cast<tob_ctx*>(c);
@@ -158,6 +159,7 @@ int tob_ctx_destroy(tob_ctx* h) {
     auto* c = reinterpret_cast<tob_ctx_impl*>(h);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    peer_teardown(c);
     if (c->comm) ncclCommDestroy(c->comm);
     for (auto& b : c->stage) b.release();
     cudaFree(c->d_partials);

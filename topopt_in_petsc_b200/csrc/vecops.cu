@@ -132,6 +132,7 @@ __global__ void k_finalize_max(const double* __restrict__ partials, int n, doubl
 }
 
 int finalize_sum_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce) {
+    if (allreduce && c->desc.nranks > 1 && finalize_allreduce(c, nblocks, nvals, d_out, 0) == 0) return 0;
     k_finalize_sum<<<1, 256, 0, c->stream>>>(c->d_partials, nblocks, d_out, nvals);
     c->launches++;
     TOB_KERNEL_CHECK();
@@ -139,6 +140,7 @@ int finalize_sum_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool
     return 0;
 }
 int finalize_max_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce) {
+    if (allreduce && c->desc.nranks > 1 && finalize_allreduce(c, nblocks, nvals, d_out, 1) == 0) return 0;
     k_finalize_max<<<1, 256, 0, c->stream>>>(c->d_partials, nblocks, d_out, nvals);
     c->launches++;
     TOB_KERNEL_CHECK();
