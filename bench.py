@@ -88,7 +88,8 @@ class DesignLoop:
         from topopt_in_petsc_b200 import Filter, LinearElasticity, MMA, solver_opts
         self.ctx, self.resident = ctx, resident
         c = CFG
-        self.phys = LinearElasticity(ctx, nu=c["nu"], opts=solver_opts(pc=pc, nlvls=nlvls, rtol=c["rtol"], coarse_its=60,
+        self.phys = LinearElasticity(ctx, nu=c["nu"], opts=solver_opts(pc=pc, nlvls=nlvls, rtol=c["rtol"], cheb_degree=3,
+                                                                       coarse_its=20 if nlvls >= 5 else 60,
                                                                        maxits=100000 if pc == 0 else 500, check_every=50))
         self.phys.SetProfile(profile)
         dx = 2.0 / c["nex"]
@@ -199,8 +200,10 @@ def run_ours(args):
         return float(ms.item()), clocks, loop.pcg_its[nwarm:]
 
     K, W = args.steps, args.warmup
-    nlv = 4
-    while nlv > 2 and (c["nez"] // world) % (1 << (nlv - 1)):
+    # deepest hierarchy (<= 6 levels) whose coarsening divides the grid and keeps the z-slab boundaries aligned
+    # (profiles/r01_gmg_sweep_192x96x96.txt: 6 levels + 20 coarse iterations beat 4 levels + 60 by 2-3x)
+    nlv = 6
+    while nlv > 2 and any(d % (1 << (nlv - 1)) for d in (c["nex"], c["ney"], c["nez"], c["nez"] // world)):
         nlv -= 1
     main_pc = 1 if args.solver == "gmg" else 0
     # ---- device-resident arm -----------------------------------------------------------------
@@ -222,7 +225,8 @@ def run_ours(args):
         loop3 = DesignLoop(ctx, resident=True, pc=1, nlvls=nlv)
         ms3, _, its3 = timed(loop3, K, W)
         gmg = {"value": K / (ms3 * 1e-3), "unit": "design iterations/s (whole job)", "ms_per_step": ms3 / K, "nlvls": nlv,
-               "pcg_iterations_per_step": its3, "smoother": "Chebyshev-Jacobi degree 4", "coarse": "60 Jacobi-PCG iterations",
+               "pcg_iterations_per_step": its3, "smoother": "Chebyshev-Jacobi degree 3",
+               "coarse": f"{20 if nlv >= 5 else 60} Jacobi-PCG iterations",
                "final_fx": loop3.hist[-1]["fx"]}
         loop3.close()
 

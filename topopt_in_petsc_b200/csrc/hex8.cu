@@ -433,19 +433,20 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         o1 = b01 * in0 + b11 * in1 + b12 * in2;
                         o2 = b02 * in0 + b12 * in1 + b22 * in2;
                     }
-                    yh[0][rho ^ 1] = Ee * o0;
-                    yh[1][rho ^ 2] = Ee * o1;
-                    yh[2][rho ^ 4] = Ee * o2;
+                    yh[0][rho ^ 1] = o0;  // the modulus is applied in the Z' stage below (one FMA instead of mul + add)
+                    yh[1][rho ^ 2] = o1;
+                    yh[2][rho ^ 4] = o2;
                 }
-                // Z' stage + face totals (lower face of this element + upper face of the previous one)
+                // Z' stage + face totals (lower face of this element + upper face of the previous one), scaled by E
                 double ht[3][4];
 #pragma unroll
                 for (int c = 0; c < 3; c++)
 #pragma unroll
                     for (int f = 0; f < 4; f++) {
-                        ht[c][f] = (yh[c][f] + yh[c][4 + f]) + (SMEM_STATE ? ups[(4 * c + f) * NT] : upr[4 * c + f]);
-                        if (SMEM_STATE) ups[(4 * c + f) * NT] = yh[c][f] - yh[c][4 + f];
-                        else upr[4 * c + f] = yh[c][f] - yh[c][4 + f];
+                        const double sl = yh[c][f] + yh[c][4 + f], su2 = yh[c][f] - yh[c][4 + f];
+                        ht[c][f] = fma(Ee, sl, SMEM_STATE ? ups[(4 * c + f) * NT] : upr[4 * c + f]);
+                        if (SMEM_STATE) ups[(4 * c + f) * NT] = Ee * su2;
+                        else upr[4 * c + f] = Ee * su2;
                     }
                 // Y' stage: row j part stays, row j+1 part goes to the thread above
                 if (FLAGS && ty + 1 <= TY - 2 && t >= L::XCH_DEPTH)  // the reader must be done with this slot's old data
@@ -611,7 +612,10 @@ static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& 
 
 int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     if (nparts) *nparts = 0;
-    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM8R : a.kernel;
+    // measured (profiles/r01_spmv_probe_l2flushed_v2.txt): 32x16 tiles / 1 CTA per SM win on slabs of a few million
+    // elements (fewer tile-overlap flops, fewer CTAs), 32x8 tiles / 2 CTAs per SM on large slabs
+    const long long slab_elems = (long long)g.nex * g.ney * (g.zl_own1() - g.zl_own0());
+    int kernel = a.kernel == SPMV_AUTO ? (slab_elems < (6LL << 20) ? SPMV_ZM16R : SPMV_ZM8R) : a.kernel;
     if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
     if (kernel == SPMV_NAIVE) {
         if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");
@@ -629,6 +633,7 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
     if (kernel == SPMV_ZM8RF) return dispatch_zm<8, false, true>(c, g, op, a, nparts);
     if (kernel == SPMV_ZM16RF) return dispatch_zm<16, false, true>(c, g, op, a, nparts);
     if (kernel == SPMV_ZM12RF) return dispatch_zm<12, false, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16R) return dispatch_zm<16, false, false>(c, g, op, a, nparts);
     return dispatch_zm<8, true, false>(c, g, op, a, nparts);
 }
 
