@@ -91,7 +91,8 @@ class DesignLoop:
         self.phys = LinearElasticity(ctx, nu=c["nu"], opts=solver_opts(pc=pc, nlvls=nlvls, rtol=c["rtol"], cheb_degree=3,
                                                                        coarse_its=20 if nlvls >= 5 else 60,
                                                                        maxits=100000 if pc == 0 else 500, check_every=50))
-        self.phys.SetProfile(profile)
+        # every 8th fine-level SpMV launch is bracketed by CUDA events (timing all of them costs ~6 % of the step)
+        self.phys.SetProfile(0 if (not profile or os.environ.get("TOB_BENCH_NOPROFILE")) else 8)
         dx = 2.0 / c["nex"]
         self.flt = Filter(ctx, 1, c["rmin_cells"] * dx)
         self.mma = MMA(ctx, 1)
@@ -255,9 +256,9 @@ def run_ours(args):
             "roofline": {"kernel": "k_hex8_zmarch (fine-level matrix-free hex8 SpMV, fp64)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "peak_kind": kind, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": alg, "launches_timed": spmv_n,
+                         "algorithmic_bytes_per_launch": alg, "launches_timed": spmv_n, "timed_every": 8,
                          "avg_launch_us": (spmv_s / spmv_n * 1e6) if spmv_n else None,
-                         "share_of_step": (spmv_s / (ms * 1e-3)) if spmv_s else None},
+                         "share_of_step": (8 * spmv_s / (ms * 1e-3)) if spmv_s else None},
             "history": [{k: (round(v, 9) if isinstance(v, float) else v) for k, v in h.items()} for h in hist[W:]],
             "gmg_solver": gmg,
         }

@@ -119,7 +119,8 @@ int tob_elast_set_state(tob_elast* h, const double* U);
 int tob_elast_get_rhs(tob_elast* h, double* rhs);
 int tob_elast_last_stats(tob_elast* h, tob_solve_stats* s);
 int tob_elast_set_opts(tob_elast* h, const tob_solver_opts* opts);
-/* time every fine-level SpMV launch of the next solves with CUDA event pairs (tob_solve_stats.spmv_seconds) */
+/* on = 1: time every fine-level SpMV launch of the next solves with CUDA event pairs (tob_solve_stats.spmv_seconds,
+ * spmv_timed); on = k > 1: time every k-th launch; 0 = off */
 int tob_elast_set_profile(tob_elast* h, int on);
 
 /* ---- Filter / PDEFilt ------------------------------------------------ */

@@ -188,3 +188,58 @@ def test_gmg_pcg_matches_direct(oracle, dens):
     Ug = mg.GetStateField()
     assert np.abs(Ug - U).max() <= 1e-5 * np.abs(U).max()
     jac.close(); mg.close(); ctx.close()
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (3, 2, 4), (5, 3, 2), (2, 7, 3), (31, 2, 2)])
+def test_tiny_and_ragged_grids(oracle, shape):
+    """Edge cases: single-element directions, grids smaller than one tile, odd sizes."""
+    from topopt_in_petsc_b200 import Context, Filter, LinearElasticity, solver_opts
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(9)
+    g = oracle.Grid(*shape)
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N, RHS = oracle.cantilever_bc_load(g)
+    x = rng.uniform(0.2, 1.0, g.nel)
+    E = oracle.simp_modulus(x, 1e-9, 1.0, 3.0)
+    u = rng.uniform(-1, 1, g.ndof)
+    yref = oracle.spmv_matrix_free(g, KE, E, N, u)
+    ctx = Context(*shape)
+    assert (ctx.nel, ctx.ndof) == (g.nel, g.ndof)
+    for kernel in (1, 5, 9):
+        phys = LinearElasticity(ctx, opts=solver_opts(spmv_kernel=kernel, rtol=1e-12, maxits=5000))
+        phys.SetDensity(x, 1e-9, 1.0, 3.0)
+        assert np.abs(phys.SpMV(u) - yref).max() <= 1e-12 * np.abs(yref).max()
+        phys.close()
+    phys = LinearElasticity(ctx, opts=solver_opts(rtol=1e-12, maxits=5000))
+    K = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N)
+    U = spla.spsolve(K.tocsc(), N * RHS)
+    df, dg = np.empty(g.nel), np.empty(g.nel)
+    fx, gx = phys.ComputeObjectiveConstraintsSensitivities(df, dg, x, 1e-9, 1.0, 3.0, 0.12)
+    fx0, gx0, df0, _ = oracle.objective_sens(g, KE, U, x, 1e-9, 1.0, 3.0, 0.12)
+    assert abs(fx - fx0) <= 1e-8 * abs(fx0) and np.abs(df - df0).max() <= 1e-7 * np.abs(df0).max()
+    fo = oracle.FilterOracle(g, 1, 0.6)
+    f = Filter(ctx, 1, 0.6)
+    xt, xp = np.empty(g.nel), np.empty(g.nel)
+    f.FilterProject(x, xt, xp, False, 1.0, 0.0)
+    assert np.abs(xt - fo.filter_project(x, False, 1.0, 0.0)[0]).max() <= 1e-13
+    f.close(); phys.close(); ctx.close()
+
+
+def test_error_paths():
+    """Error convention: non-zero return + message, no crash (the reference returns PetscErrorCode)."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, Filter, TobError, solver_opts
+    with pytest.raises(TobError):
+        Context(1, 5, 5)
+    ctx = Context(9, 5, 5)
+    phys = LinearElasticity(ctx)
+    with pytest.raises(TobError):
+        phys.SpMV(np.zeros(ctx.ndof))          # density not set yet
+    with pytest.raises(TobError):
+        LinearElasticity(ctx, opts=solver_opts(pc=1, nlvls=4))  # 8x4x4 elements cannot be coarsened 3 times
+    f = Filter(ctx, 7, 0.1)                    # unknown filter type = no filtering (Filter.cc:104-107)
+    x = np.linspace(0, 1, ctx.nel); xt, xp = np.empty(ctx.nel), np.empty(ctx.nel)
+    f.FilterProject(x, xt, xp, False, 1.0, 0.0)
+    assert np.array_equal(xt, x) and np.array_equal(xp, x)
+    with pytest.raises(TobError):
+        f.GetHs()
+    f.close(); phys.close(); ctx.close()

@@ -211,7 +211,7 @@ class LinearElasticity:
         return r
 
     def SetProfile(self, on=True):
-        check(self.lib.tob_elast_set_profile(self.h, 1 if on else 0))
+        check(self.lib.tob_elast_set_profile(self.h, int(on)))
 
     def stats(self) -> SolveStats:
         s = SolveStats()

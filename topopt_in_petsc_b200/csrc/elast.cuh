@@ -28,6 +28,7 @@ struct tob_elast_impl {
     GmgHierarchy* mg = nullptr;
     // optional per-launch SpMV timing (bench.py roofline): event pairs recorded around each launch
     bool profile = false;
+    int prof_stride = 1;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
 };

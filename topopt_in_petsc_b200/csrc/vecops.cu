@@ -306,6 +306,107 @@ int vec_fill(tob_ctx_impl* c, double* y, double v, long long n) {
     return 0;
 }
 
+// ---- single-rank Jacobi-PCG without finalize kernels --------------------------------------------------------
+// The two 1-CTA finalize launches per iteration (and their dependency gaps) cost ~18 us of a ~157 us iteration at
+// 192x96x96 (profiles/r01_bench_launches_cfg2.csv).  On one GPU the consumers can reduce the producer's per-CTA
+// partial sums themselves: every CTA sums the same <= few-thousand doubles in the same order, so all CTAs compute
+// bitwise identical alpha / beta.  Layout of an "xr partial block": [0,nb) = r.r, [nb,2nb) = r.dinv.r.
+__device__ __forceinline__ double sum_parts_bcast(const double* __restrict__ p, int n, double* red, double* bc) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += p[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *bc = s;
+    __syncthreads();
+    s = *bc;
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(kFlatThreads)
+k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
+                  const double* __restrict__ dinv, long long n, const double* __restrict__ pq_parts, int n_pq,
+                  const double* __restrict__ prev_parts, int nb_prev, double* __restrict__ out_parts) {
+    __shared__ double red[32];
+    __shared__ double bc;
+    double alpha = 0.0;  // pq_parts == nullptr: the initial pass that only forms r.r and r.dinv.r
+    if (pq_parts) {
+        const double pq = sum_parts_bcast(pq_parts, n_pq, red, &bc);
+        const double rz = sum_parts_bcast(prev_parts + nb_prev, nb_prev, red, &bc);
+        alpha = rz / pq;
+    }
+    double rr = 0.0, rz2 = 0.0;
+    long long n2 = n >> 1;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    const double2* q2 = reinterpret_cast<const double2*>(q);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 rv = r2[i];
+        if (pq_parts) {
+            double2 xv = x2[i], pv = p2[i], qv = q2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
+            x2[i] = xv; r2[i] = rv;
+        }
+        const double2 dv = d2[i];
+        rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
+        rz2 = fma(rv.x * dv.x, rv.x, rz2); rz2 = fma(rv.y * dv.y, rv.y, rz2);
+    }
+    rr = block_sum(rr, red);
+    rz2 = block_sum(rz2, red);
+    if (threadIdx.x == 0) { out_parts[blockIdx.x] = rr; out_parts[gridDim.x + blockIdx.x] = rz2; }
+}
+
+__global__ void __launch_bounds__(kFlatThreads)
+k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ dinv, long long n,
+                 const double* __restrict__ new_parts, const double* __restrict__ old_parts, int nb) {
+    __shared__ double red[32];
+    __shared__ double bc;
+    double beta = 0.0;  // old_parts == nullptr: first direction p = dinv r
+    if (old_parts) {
+        const double rz_new = sum_parts_bcast(new_parts + nb, nb, red, &bc);
+        const double rz_old = sum_parts_bcast(old_parts + nb, nb, red, &bc);
+        beta = rz_new / rz_old;
+    }
+    long long n2 = n >> 1;
+    double2* p2 = reinterpret_cast<double2*>(p);
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 rv = r2[i], dv = d2[i];
+        double2 pv = old_parts ? p2[i] : make_double2(0.0, 0.0);
+        pv.x = fma(beta, pv.x, rv.x * dv.x); pv.y = fma(beta, pv.y, rv.y * dv.y);
+        p2[i] = pv;
+    }
+}
+
+int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const double* dinv,
+                    const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out) {
+    const int nb = flat_grid(c, g.own_len);
+    k_pcg_update_xr_f<<<nb, kFlatThreads, 0, c->stream>>>(x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off, dinv + g.own_off,
+                                                        g.own_len, pq_parts, n_pq, prev_parts, nb, out_parts);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    if (nb_out) *nb_out = nb;
+    return 0;
+}
+int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const double* dinv, const double* new_parts,
+                   const double* old_parts) {
+    const int nb = flat_grid(c, g.own_len);
+    k_pcg_update_p_f<<<nb, kFlatThreads, 0, c->stream>>>(p + g.own_off, r + g.own_off, dinv + g.own_off, g.own_len, new_parts, old_parts, nb);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+// sum an xr partial block into two consecutive scalar slots (host convergence checks)
+int finalize_parts(tob_ctx_impl* c, const double* parts, int nb, int slot) {
+    k_finalize_sum<<<1, 256, 0, c->stream>>>(parts, nb, c->d_scalars + slot, 2);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
 }  // namespace tob
 
 extern "C" int tob_vec_scale(tob_ctx* ctx, double* v, double a, long long n) {
