@@ -29,6 +29,10 @@ struct tob_elast_impl {
     // optional per-launch SpMV timing (bench.py roofline): event pairs recorded around each launch
     bool profile = false;
     int prof_stride = 1;
+    // CUDA graph of a block of multi-GPU Jacobi-PCG iterations (elast.cu)
+    cudaGraphExec_t pcg_graph = nullptr;
+    int pcg_graph_its = 0;
+    long long pcg_graph_launches = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
 };
