@@ -76,6 +76,9 @@ int tob_ctx_sizes(tob_ctx* ctx, long long* nel_owned, long long* ndof_owned, lon
                   long long* ndof_global);
 /* owned global z ranges of this slab: node planes [kn0,kn1), element layers [ke0,ke1) (LinearElasticity.cc:804-818) */
 int tob_ctx_slab(tob_ctx* ctx, int* kn0, int* kn1, int* ke0, int* ke1);
+/* the same ownership rule as a pure host function (no device needed): what rank `rank` of `nranks` z-slabs owns
+ * on a grid with nzn node planes.  Replaces the DMDA ownership ranges the reference reads with DMDAGetCorners. */
+int tob_slab_partition(int nzn, int nranks, int rank, int* kn0, int* kn1, int* ke0, int* ke1);
 int tob_ctx_sync(tob_ctx* ctx);
 long long tob_ctx_launch_count(tob_ctx* ctx, int reset);
 void* tob_ctx_stream(tob_ctx* ctx);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "tob_ctx_destroy": (_I, [_P]),
     "tob_ctx_sizes": (_I, [_P, _PLL, _PLL, _PLL, _PLL]),
     "tob_ctx_slab": (_I, [_P, _PI, _PI, _PI, _PI]),
+    "tob_slab_partition": (_I, [_I, _I, _I, _PI, _PI, _PI, _PI]),
     "tob_ctx_sync": (_I, [_P]),
     "tob_ctx_launch_count": (_LL, [_P, _I]),
     "tob_ctx_stream": (_P, [_P]),

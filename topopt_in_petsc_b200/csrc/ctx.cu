@@ -126,10 +126,8 @@ int tob_ctx_create(const tob_grid_desc* d, tob_ctx** out) {
     TOB_CUDA(cudaEventCreate(&c->ev0));
     TOB_CUDA(cudaEventCreate(&c->ev1));
     // z-slab partition: element layers split evenly, rank 0 additionally owns node plane 0
-    const int nez = d->nzn - 1;
-    auto e_start = [&](int r) { return (int)((long long)nez * r / d->nranks); };
-    const int es = e_start(d->rank), ee = e_start(d->rank + 1);
-    const int kn0 = d->rank == 0 ? 0 : es + 1, kn1 = ee + 1;
+    int kn0 = 0, kn1 = 0;
+    TOB_CHECK(tob_slab_partition(d->nzn, d->nranks, d->rank, &kn0, &kn1, nullptr, nullptr));
     const double dx = (d->xc[1] - d->xc[0]) / (d->nxn - 1);  // TopOpt.cc:225-227
     const double dy = (d->xc[3] - d->xc[2]) / (d->nyn - 1);
     const double dz = (d->xc[5] - d->xc[4]) / (d->nzn - 1);
@@ -151,6 +149,19 @@ int tob_ctx_create(const tob_grid_desc* d, tob_ctx** out) {
     }
     TOB_CUDA(cudaStreamSynchronize(c->stream));
     *out = reinterpret_cast<tob_ctx*>(c);
+    return 0;
+}
+
+int tob_slab_partition(int nzn, int nranks, int rank, int* kn0, int* kn1, int* ke0, int* ke1) {
+    if (nzn < 2 || nranks < 1 || rank < 0 || rank >= nranks) TOB_FAIL("bad slab partition arguments");
+    if (nzn - 1 < nranks) TOB_FAIL("fewer element layers than z-slabs");
+    const int nez = nzn - 1;
+    const int es = (int)((long long)nez * rank / nranks), ee = (int)((long long)nez * (rank + 1) / nranks);
+    const int n0 = rank == 0 ? 0 : es + 1, n1 = ee + 1;
+    if (kn0) *kn0 = n0;
+    if (kn1) *kn1 = n1;
+    if (ke0) *ke0 = es;   // == (rank == 0 ? 0 : n0 - 1): elements follow their upper node plane
+    if (ke1) *ke1 = ee;
     return 0;
 }
 
