@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtopopt_b200.so")
+# TOB_LIB_PATH: load another build of the same library (A/B kernel experiments); default = the in-tree build
+LIB_PATH = os.environ.get("TOB_LIB_PATH") or os.path.join(_HERE, "libtopopt_b200.so")
 
 
 class TobError(RuntimeError):

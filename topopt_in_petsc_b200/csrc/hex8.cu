@@ -184,13 +184,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void lds2(double& a, double& b, uint32_t addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
@@ -240,24 +235,30 @@ struct ZmSmem {
     static constexpr int E_BYTES = (NC * 8 + 127) / 128 * 128;
     static constexpr int TX_BYTES = 4 * NC * 8;                     // bytes the two TMA loads deliver per stage
     static constexpr int STAGE_BYTES = U_BYTES + E_BYTES;
-    static constexpr int XCH_DEPTH = FLAGS ? 4 : 2;               // exchange-buffer ring (y-neighbour hand-off)
+    // TMA ring depth (a plane is consumed by exactly one step, so the prefetch distance is STAGES-1 planes); the
+    // register-state variants have shared memory to spare for a deeper ring.
+    static constexpr int STAGES = FLAGS ? 4 : (SMEM_STATE ? 4 : 6);
+    // exchange-buffer ring (y-neighbour hand-off).  FLAGS: no reverse (reader -> writer) signal exists; a row can
+    // start step t only after every row finished step t - STAGES (that is when the producer may refill the slot
+    // of plane t + 1), so a ring of STAGES exchange slots can never be overwritten before it was read.
+    static constexpr int XCH_DEPTH = FLAGS ? STAGES : 2;
     static constexpr int XCH_BYTES = XCH_DEPTH * 6 * NT * 8;
     static constexpr int UP_BYTES = SMEM_STATE ? 24 * NT * 8 : 0;  // carried state when kept out of registers
-    // TMA ring depth: with the delayed refill (the plane below is re-read for the output) the prefetch
-    // distance is STAGES-2 planes; the register-state variants have shared memory to spare for a deeper ring.
-    static constexpr int STAGES = SMEM_STATE ? 4 : 6;
     static constexpr int KB_OFF = STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;  // 48 block constants
     static constexpr int BAR_OFF = KB_OFF + 48 * 8;
-    static constexpr int FLAG_OFF = BAR_OFF + STAGES * 8 + 64;       // row sequence / completion counters
-    static constexpr int TOTAL = FLAG_OFF + 2 * 32 * 4 + 128;
+    // mbarriers: full[STAGES]; FLAGS adds empty[STAGES] and xfull[TY][XCH_DEPTH]
+    static constexpr int NBARS = STAGES + (FLAGS ? STAGES + TY * XCH_DEPTH : 0);
+    static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 128;
 };
 
 // SMEM_STATE: the 24 doubles carried from one z-step to the next (lower-face modes + upper-face
 // contributions) live in shared memory (lets two 256-thread CTAs share an SM at 128 registers) or in
 // registers (one CTA per SM with a larger register budget; less shared-memory traffic).
-// FLAGS: instead of one __syncthreads per z-step, warp row ty waits only for row ty-1 (per-row sequence
-// counters in shared memory, st.release / ld.acquire); ring slots are recycled when every row's completion
-// counter has passed them.  ncu on the barrier version: 1.5 of ~4 resident warps per scheduler sat at the barrier.
+// FLAGS: no CTA-wide barrier inside the march.  Warp row ty hands its y-exchange data to row ty+1 through one
+// mbarrier per (row, exchange slot); the top row (which has no elements of its own) is the TMA producer and
+// recycles a ring slot when all TY-1 consumer rows have arrived on its "empty" mbarrier.  Waiting warps sit in
+// mbarrier.try_wait (hardware-suspended), not in a shared-memory spin loop -- the earlier spin-flag version of this
+// idea ran 2.4x slower than the barrier kernel (profiles/r01_ncu_zmarch_ty8_flags_256.txt).
 template <int TY, int EPI, bool SMEM_STATE, bool FLAGS>
 __global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
 k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
@@ -266,19 +267,20 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
     constexpr int NT = L::NT;
     constexpr int NC = L::NC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    int* rowseq = reinterpret_cast<int*>(smem_raw + L::FLAG_OFF);  // [ty] = steps whose y-hand-off data is published
-    int* rowdone = rowseq + 32;                                    // [ty] = steps completely finished
     __shared__ double red[32];
     double* xch = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES);
     double* ups = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES + L::XCH_BYTES) + (threadIdx.x);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);  // full[STAGES]
+    uint64_t* ebars = bars + L::STAGES;                                   // FLAGS: empty[STAGES]
+    uint64_t* xbars = bars + 2 * L::STAGES;                               // FLAGS: xfull[TY][XCH_DEPTH]
     // symmetric 3x3 blocks, 6 unique entries each (b00 b01 b02 b11 b12 b22), read back with broadcast
     // ld.shared.v2.f64: keeping 72 constants in uniform registers made the loop issue-bound.
     double* kbs = reinterpret_cast<double*>(smem_raw + L::KB_OFF);
     const uint32_t kb_addr = smem_u32(kbs);
 
     const int tid = threadIdx.x;
-    const int tx = tid & 31, ty = tid >> 5;
+    const int tx = tid & 31;
+    const int ty = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp row; the broadcast lets ptxas treat it as warp-uniform
     const int i0 = blockIdx.x * 30 - 1, j0 = blockIdx.y * (TY - 2) - 1;
     const int i = i0 + tx, j = j0 + ty;
     const int z0 = P.zout0 + blockIdx.z * P.zchunk;
@@ -295,9 +297,12 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             const int r = k < 3 ? 0 : (k < 5 ? 1 : 2), cc = k < 3 ? k : (k < 5 ? k - 2 : 2);
             kbs[tid] = KB.b[rho][3 * r + cc];
         }
-        if (tid < 64) rowseq[tid] = (tid >= 32 + TY - 1) ? 0x3fffffff : 0;  // the idle top row never blocks a refill
         if (tid == 0) {
             for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
+            if (FLAGS) {
+                for (int s = 0; s < L::STAGES; s++) mbar_init(&ebars[s], TY - 1);
+                for (int s = 0; s < TY * L::XCH_DEPTH; s++) mbar_init(&xbars[s], 1);
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -316,21 +321,23 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         auto load_mask = [&](int p) -> unsigned {
             return (innode && p >= 0 && p < P.nzl) ? (unsigned)P.mask[(long long)p * P.mstride + (long long)j * P.pm + i] : 0u;
         };
-        int issued = 0;  // (thread 0) next plane counter to issue
-        if (tid == 0)
-            for (; issued < L::STAGES && issued < nplanes; issued++) issue(issued);
-        // FLAGS: plane q may overwrite ring slot q % STAGES once every row finished step q - STAGES (the step that
-        // re-reads plane q - STAGES for its output), i.e. all rowdone >= q - STAGES + 1.
-        auto min_done = [&]() {
-            int m = 0x3fffffff;
-#pragma unroll
-            for (int r = 0; r < TY - 1; r++) m = min(m, ld_acquire(&rowdone[r]));
-            return m;
-        };
+        if (FLAGS) {
+            // producer row: plane q reuses the slot of plane q - STAGES, which every consumer row releases at the end
+            // of the step that consumed it (step q - STAGES - 1; the prologue for plane 0)
+            if (ty == TY - 1) {
+                for (int q = 0; q < nplanes; q++) {  // whole warp waits (keeps the warp converged), lane 0 issues
+                    if (q >= L::STAGES) mbar_wait(&ebars[q % L::STAGES], ((q / L::STAGES) - 1) & 1);
+                    if (tx == 0) issue(q);
+                }
+            }
+        } else if (tid == 0) {
+            for (int q = 0; q < L::STAGES && q < nplanes; q++) issue(q);
+        }
 
         double* fps = ups + 12 * NT;  // face modes of the lower plane of the current element
         double fpr[12], upr[12];      // register copies of the carried state (SMEM_STATE == false)
         unsigned mown = 0;
+        double uown[3] = {0.0, 0.0, 0.0};  // my nodal value on the plane completed by the current step
 #pragma unroll
         for (int k = 0; k < 12; k++) {
             if (SMEM_STATE) { ups[k * NT] = 0.0; fps[k * NT] = 0.0; }
@@ -340,7 +347,9 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         const int o2 = ty * 32 + tx;       // my slot in the exchange buffers
 
         // face modes of one plane tile: X stage on rows j and j+1, then Y stage
-        auto face_modes = [&](const unsigned char* st, double (&fm)[3][4]) {
+        // (also hands back my own nodal value: it is the Dirichlet / dot-product operand of the NEXT step's output,
+        // kept in registers instead of being re-read from the ring)
+        auto face_modes = [&](const unsigned char* st, double (&fm)[3][4], double (&own)[3]) {
             const double* su = reinterpret_cast<const double*>(st);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -350,17 +359,18 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 fm[c][1] = d0 + d1;
                 fm[c][2] = s0 - s1;
                 fm[c][3] = d0 - d1;
+                own[c] = a;
             }
         };
 
         // ---- prologue: plane pfirst ------------------------------------------------------
-        {
+        if (!FLAGS || ty < TY - 1) {
             mbar_wait(&bars[0], 0);
             const unsigned char* st = smem_raw;
             mown = load_mask(pfirst);
             if (compute) {
                 double f0[3][4];
-                face_modes(st, f0);
+                face_modes(st, f0, uown);
 #pragma unroll
                 for (int c = 0; c < 3; c++)
 #pragma unroll
@@ -369,30 +379,37 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         else fpr[4 * c + f] = f0[c][f];
                     }
             }
+            if (FLAGS) {
+                __syncwarp();
+                if (tx == 0) mbar_arrive(&ebars[0]);
+            }
         }
 
         // ---- march: step t handles element layer e = pfirst + t, upper plane pfirst + t + 1 -----
         const int nsteps = z1 - pfirst;
+        if (!FLAGS || ty < TY - 1)
         for (int t = 0; t < nsteps; t++) {
             const int pidx = t + 1;
             const int s = pidx % L::STAGES;
             const unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const unsigned mnew = load_mask(pfirst + pidx);  // consumed one step later
-            if (FLAGS) {
-                if (ty == TY - 1) continue;  // idle row: nothing to compute, nothing to hand over
-                if (tid == 0)
-                    while (issued <= pidx) {  // my own next plane is not in flight yet: wait for the slowest row
-                        while (min_done() < issued - L::STAGES + 1) {}
-                        issue(issued++);
-                    }
-            }
             mbar_wait(&bars[s], (pidx / L::STAGES) & 1);
 
+#ifndef TOB_KB_LDS
+            // Block constants straight from the kernel-parameter constant bank as uniform-register operands of the
+            // DP instructions (SASS: LDCU.64 c[0x0][UR+imm] ... DFMA R, R, UR, R).  The index carries a term that is
+            // zero for every reachable t but opaque to ptxas: with a loop-invariant address it hoists all 48 loads
+            // and then thrashes the 63 uniform registers (R2UR spills); re-loading per step keeps the shared-memory
+            // pipe (the co-limiting unit next to FP64: 24 of ~95 wavefronts per warp-step were these constants)
+            // and 12 vector registers free.
+            const double* kz = &KB.b[0][0] + (t >> 30);
+#endif
             double ex0[3][2];  // edge (row j) contributions of my face
+            double unew[3] = {0.0, 0.0, 0.0};
             double* xw = xch + (t % L::XCH_DEPTH) * 6 * NT;
             if (compute) {
                 double fnew[3][4];
-                face_modes(st, fnew);
+                face_modes(st, fnew, unew);
                 const double Ee = reinterpret_cast<const double*>(st + L::U_BYTES)[o];
                 // Z stage: element modes  uh[c][ma + 2 mb + 4 mg]
                 double uh[3][8];
@@ -412,9 +429,14 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 for (int rho = 0; rho < 8; rho++) {
                     const double in0 = uh[0][rho ^ 1], in1 = uh[1][rho ^ 2], in2 = uh[2][rho ^ 4];
                     double b00, b01, b02, b11, b12, b22;
+#ifdef TOB_KB_LDS
                     lds2(b00, b01, kb_addr + rho * 48);
                     lds2(b02, b11, kb_addr + rho * 48 + 16);
                     lds2(b12, b22, kb_addr + rho * 48 + 32);
+#else
+                    b00 = kz[rho * 9 + 0]; b01 = kz[rho * 9 + 1]; b02 = kz[rho * 9 + 2];
+                    b11 = kz[rho * 9 + 4]; b12 = kz[rho * 9 + 5]; b22 = kz[rho * 9 + 8];
+#endif
                     double o0, o1, o2;
                     if (rho == 1) {
                         o0 = 0.0;
@@ -449,8 +471,6 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         else upr[4 * c + f] = Ee * su2;
                     }
                 // Y' stage: row j part stays, row j+1 part goes to the thread above
-                if (FLAGS && ty + 1 <= TY - 2 && t >= L::XCH_DEPTH)  // the reader must be done with this slot's old data
-                    while (ld_acquire(&rowdone[ty + 1]) < t - L::XCH_DEPTH + 1) {}
 #pragma unroll
                 for (int c = 0; c < 3; c++)
 #pragma unroll
@@ -464,12 +484,12 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             }
             if (FLAGS) {
                 __syncwarp();
-                if (tx == 0) st_release(&rowseq[ty], t + 1);
-                if (ty >= 1) while (ld_acquire(&rowseq[ty - 1]) < t + 1) {}
+                if (tx == 0 && ty < TY - 2) mbar_arrive(&xbars[ty * L::XCH_DEPTH + t % L::XCH_DEPTH]);
+                if (ty >= 1) mbar_wait(&xbars[(ty - 1) * L::XCH_DEPTH + t % L::XCH_DEPTH], (t / L::XCH_DEPTH) & 1);
             } else {
                 __syncthreads();
-                // the ring slot of plane pidx-2 is free now (plane pidx-1 is still read below for the output)
-                if (tid == 0 && pidx >= 2 && pidx - 2 + L::STAGES < nplanes) issue(pidx - 2 + L::STAGES);
+                // every thread is past plane t (consumed by step t-1 / the prologue): refill its ring slot
+                if (tid == 0 && t + L::STAGES < nplanes) issue(t + L::STAGES);
             }
 
             // edge totals, X' stage, node totals
@@ -489,12 +509,11 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 
             const int e = pfirst + t;  // node plane completed by this step
             if (outthr && e >= z0) {
-                const double* sl = reinterpret_cast<const double*>(smem_raw + (t % L::STAGES) * L::STAGE_BYTES);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const long long idx = e * P.pstride + c * P.nstride + (long long)j * P.px + i;
                     const bool fixed = (mown >> c) & 1u;
-                    const double uo = sl[c * NC + o];  // own nodal value on plane e (still in the ring)
+                    const double uo = uown[c];  // own nodal value on plane e
                     const double au = fixed ? uo : v[c];
                     if (EPI == EPI_Y) {
                         P.y[idx] = au;
@@ -514,11 +533,11 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 }
             }
             mown = mnew;
-            if (FLAGS) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) uown[c] = unew[c];
+            if (FLAGS) {  // this row is done with plane pidx and with the exchange slot of step t
                 __syncwarp();
-                if (tx == 0) st_release(&rowdone[ty], t + 1);
-                if (tid == 0)  // opportunistic refill of every ring slot that all rows have left
-                    while (issued < nplanes && min_done() >= issued - L::STAGES + 1) issue(issued++);
+                if (tx == 0) mbar_arrive(&ebars[pidx % L::STAGES]);
             }
         }
     }
@@ -612,10 +631,9 @@ static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& 
 
 int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     if (nparts) *nparts = 0;
-    // measured (profiles/r01_spmv_probe_l2flushed_v2.txt): 32x16 tiles / 1 CTA per SM win on slabs of a few million
-    // elements (fewer tile-overlap flops, fewer CTAs), 32x8 tiles / 2 CTAs per SM on large slabs
-    const long long slab_elems = (long long)g.nex * g.ney * (g.zl_own1() - g.zl_own0());
-    int kernel = a.kernel == SPMV_AUTO ? (slab_elems < (6LL << 20) ? SPMV_ZM16R : SPMV_ZM8R) : a.kernel;
+    // measured (profiles/r01_spmv_probe_v4.txt): the mbarrier hand-off kernel with 32x16 tiles wins at every size tried
+    // (192x96x96: 49 us vs 54 (ZM16R) / 65 (ZM8R); 256^3: 0.368 ms vs 0.422 / 0.428)
+    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM16RF : a.kernel;
     if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
     if (kernel == SPMV_NAIVE) {
         if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");
