@@ -227,7 +227,7 @@ struct ZmParams {
 // coordinate must be 16-byte aligned (measured: odd fp64 origins raise "illegal instruction"), so the
 // box starts at the even column bx*30-2 and thread tx reads column tx+1.
 constexpr int ZM_W = 34;
-template <int TY, bool SMEM_STATE = true, bool FLAGS = false>
+template <int TY, bool FLAGS>
 struct ZmSmem {
     static constexpr int NT = 32 * TY;
     static constexpr int NC = ZM_W * TY;          // doubles per component tile
@@ -235,48 +235,45 @@ struct ZmSmem {
     static constexpr int E_BYTES = (NC * 8 + 127) / 128 * 128;
     static constexpr int TX_BYTES = 4 * NC * 8;                     // bytes the two TMA loads deliver per stage
     static constexpr int STAGE_BYTES = U_BYTES + E_BYTES;
-    // TMA ring depth (a plane is consumed by exactly one step, so the prefetch distance is STAGES-1 planes); the
-    // register-state variants have shared memory to spare for a deeper ring.
-    static constexpr int STAGES = FLAGS ? 4 : (SMEM_STATE ? 4 : 6);
+    // TMA ring depth (a plane is consumed by exactly one step, so the prefetch distance is STAGES-1 planes)
+    static constexpr int STAGES = FLAGS ? 4 : 6;
     // exchange-buffer ring (y-neighbour hand-off).  FLAGS: no reverse (reader -> writer) signal exists; a row can
     // start step t only after every row finished step t - STAGES (that is when the producer may refill the slot
     // of plane t + 1), so a ring of STAGES exchange slots can never be overwritten before it was read.
     static constexpr int XCH_DEPTH = FLAGS ? STAGES : 2;
     static constexpr int XCH_BYTES = XCH_DEPTH * 6 * NT * 8;
-    static constexpr int UP_BYTES = SMEM_STATE ? 24 * NT * 8 : 0;  // carried state when kept out of registers
-    static constexpr int KB_OFF = STAGES * STAGE_BYTES + XCH_BYTES + UP_BYTES;  // 48 block constants
-    static constexpr int BAR_OFF = KB_OFF + 48 * 8;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES + XCH_BYTES;
     // mbarriers: full[STAGES]; FLAGS adds empty[STAGES] and xfull[TY][XCH_DEPTH]
     static constexpr int NBARS = STAGES + (FLAGS ? STAGES + TY * XCH_DEPTH : 0);
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 128;
 };
 
-// SMEM_STATE: the 24 doubles carried from one z-step to the next (lower-face modes + upper-face
-// contributions) live in shared memory (lets two 256-thread CTAs share an SM at 128 registers) or in
-// registers (one CTA per SM with a larger register budget; less shared-memory traffic).
-// FLAGS: no CTA-wide barrier inside the march.  Warp row ty hands its y-exchange data to row ty+1 through one
+// the 8 symmetric 3x3 blocks as 16-byte pairs (b00 b01 | b02 b11 | b12 b22) so that one LDCU.128 fetches two
+struct alignas(16) Hex8BlocksPacked {
+    double2 k[8][3];
+};
+
+// One CTA = 32 x TY node columns marching along z; the 24 doubles carried from one z-step to the next (lower-face
+// modes + upper-face contributions) stay in registers.
+// FLAGS = false: one __syncthreads per z-step orders the y-neighbour exchange; thread 0 refills the TMA ring.
+// FLAGS = true : no CTA-wide barrier inside the march.  Warp row ty hands its y-exchange data to row ty+1 through one
 // mbarrier per (row, exchange slot); the top row (which has no elements of its own) is the TMA producer and
 // recycles a ring slot when all TY-1 consumer rows have arrived on its "empty" mbarrier.  Waiting warps sit in
 // mbarrier.try_wait (hardware-suspended), not in a shared-memory spin loop -- the earlier spin-flag version of this
 // idea ran 2.4x slower than the barrier kernel (profiles/r01_ncu_zmarch_ty8_flags_256.txt).
-template <int TY, int EPI, bool SMEM_STATE, bool FLAGS>
+template <int TY, int EPI, bool FLAGS>
 __global__ void __launch_bounds__(32 * TY, (TY <= 8) ? 2 : 1)
 k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
-              const __grid_constant__ Hex8Blocks KB, const __grid_constant__ ZmParams P) {
-    using L = ZmSmem<TY, SMEM_STATE, FLAGS>;
+              const __grid_constant__ Hex8BlocksPacked KB, const __grid_constant__ ZmParams P) {
+    using L = ZmSmem<TY, FLAGS>;
     constexpr int NT = L::NT;
     constexpr int NC = L::NC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double red[32];
     double* xch = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES);
-    double* ups = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES + L::XCH_BYTES) + (threadIdx.x);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);  // full[STAGES]
     uint64_t* ebars = bars + L::STAGES;                                   // FLAGS: empty[STAGES]
     uint64_t* xbars = bars + 2 * L::STAGES;                               // FLAGS: xfull[TY][XCH_DEPTH]
-    // symmetric 3x3 blocks, 6 unique entries each (b00 b01 b02 b11 b12 b22), read back with broadcast
-    // ld.shared.v2.f64: keeping 72 constants in uniform registers made the loop issue-bound.
-    double* kbs = reinterpret_cast<double*>(smem_raw + L::KB_OFF);
-    const uint32_t kb_addr = smem_u32(kbs);
 
     const int tid = threadIdx.x;
     const int tx = tid & 31;
@@ -285,18 +282,15 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
     const int i = i0 + tx, j = j0 + ty;
     const int z0 = P.zout0 + blockIdx.z * P.zchunk;
     const int z1 = min(z0 + P.zchunk, P.zout1);
-    const bool compute = (tx < 31) && (ty < TY - 1);
+    // rows 0..TY-2 own an element row each (lane 31 computes a throw-away column: no divergence inside the step);
+    // row TY-1 only closes the tile: idle in the barrier variant, TMA producer in the mbarrier variant
+    const bool rowcompute = ty < TY - 1;
     const bool outthr = (tx >= 1) && (tx <= 30) && (ty >= 1) && (ty <= TY - 2) && (i < P.nxn) && (j < P.nyn);
     const int pfirst = z0 - 1;        // first node plane consumed (prologue)
     const int nplanes = z1 - z0 + 2;  // planes pfirst .. z1
     double part = 0.0;
 
     if (z0 < z1) {
-        if (tid < 48) {
-            const int rho = tid / 6, k = tid % 6;
-            const int r = k < 3 ? 0 : (k < 5 ? 1 : 2), cc = k < 3 ? k : (k < 5 ? k - 2 : 2);
-            kbs[tid] = KB.b[rho][3 * r + cc];
-        }
         if (tid == 0) {
             for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
             if (FLAGS) {
@@ -316,11 +310,6 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             tma_load_4d(st, &tmU, &bars[s], i0 - 1, j0, 0, p);
             tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
         };
-        // Dirichlet mask byte of my own node on local plane p (0 outside the grid)
-        const bool innode = (i >= 0) && (i < P.nxn) && (j >= 0) && (j < P.nyn);
-        auto load_mask = [&](int p) -> unsigned {
-            return (innode && p >= 0 && p < P.nzl) ? (unsigned)P.mask[(long long)p * P.mstride + (long long)j * P.pm + i] : 0u;
-        };
         if (FLAGS) {
             // producer row: plane q reuses the slot of plane q - STAGES, which every consumer row releases at the end
             // of the step that consumed it (step q - STAGES - 1; the prologue for plane 0)
@@ -334,82 +323,77 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             for (int q = 0; q < L::STAGES && q < nplanes; q++) issue(q);
         }
 
-        double* fps = ups + 12 * NT;  // face modes of the lower plane of the current element
-        double fpr[12], upr[12];      // register copies of the carried state (SMEM_STATE == false)
-        unsigned mown = 0;
-        double uown[3] = {0.0, 0.0, 0.0};  // my nodal value on the plane completed by the current step
-#pragma unroll
-        for (int k = 0; k < 12; k++) {
-            if (SMEM_STATE) { ups[k * NT] = 0.0; fps[k * NT] = 0.0; }
-            fpr[k] = 0.0; upr[k] = 0.0;
-        }
+        // Dirichlet mask byte of my own node, one plane per step through a running pointer (0 outside the grid)
+        const bool innode = (i >= 0) && (i < P.nxn) && (j >= 0) && (j < P.nyn);
+        const unsigned char* mptr = P.mask + ((long long)pfirst * P.mstride + (long long)j * P.pm + i);
         const int o = ty * ZM_W + tx + 1;  // my node inside a component tile
         const int o2 = ty * 32 + tx;       // my slot in the exchange buffers
 
-        // face modes of one plane tile: X stage on rows j and j+1, then Y stage
-        // (also hands back my own nodal value: it is the Dirichlet / dot-product operand of the NEXT step's output,
-        // kept in registers instead of being re-read from the ring)
-        auto face_modes = [&](const unsigned char* st, double (&fm)[3][4], double (&own)[3]) {
+        // face modes of one plane tile: X stage on rows j and j+1, then Y stage; also hands back my own nodal
+        // value (the Dirichlet / dot-product operand of the NEXT step's output, kept in registers)
+        auto face_modes = [&](const unsigned char* st, double (&fm)[12], double (&own)[3]) {
             const double* su = reinterpret_cast<const double*>(st);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const double a = su[c * NC + o], b = su[c * NC + o + 1], cc = su[c * NC + o + ZM_W], d = su[c * NC + o + ZM_W + 1];
                 const double s0 = a + b, d0 = a - b, s1 = cc + d, d1 = cc - d;
-                fm[c][0] = s0 + s1;
-                fm[c][1] = d0 + d1;
-                fm[c][2] = s0 - s1;
-                fm[c][3] = d0 - d1;
+                fm[4 * c + 0] = s0 + s1;
+                fm[4 * c + 1] = d0 + d1;
+                fm[4 * c + 2] = s0 - s1;
+                fm[4 * c + 3] = d0 - d1;
                 own[c] = a;
             }
         };
 
+        // carried state: A = plane below the current element layer, B = plane above (becomes A at the end of the step).
+        // (Unrolling the march by two with A/B swapped would save the ~30 register moves per step, but ptxas then loses
+        // the warp-uniformity of the constant loads in the mbarrier variant -- LDC into vector registers, 400 B of spills.)
+        double fA[12], fB[12], upr[12], uA[3], uB[3];
+        unsigned mA = 0, mB = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { fA[k] = 0.0; fB[k] = 0.0; upr[k] = 0.0; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { uA[c] = 0.0; uB[c] = 0.0; }
+
         // ---- prologue: plane pfirst ------------------------------------------------------
-        if (!FLAGS || ty < TY - 1) {
+        if (!FLAGS || rowcompute) {
             mbar_wait(&bars[0], 0);
-            const unsigned char* st = smem_raw;
-            mown = load_mask(pfirst);
-            if (compute) {
-                double f0[3][4];
-                face_modes(st, f0, uown);
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-#pragma unroll
-                    for (int f = 0; f < 4; f++) {
-                        if (SMEM_STATE) fps[(4 * c + f) * NT] = f0[c][f];
-                        else fpr[4 * c + f] = f0[c][f];
-                    }
-            }
+            mA = (innode && pfirst >= 0) ? (unsigned)*mptr : 0u;
+            mptr += P.mstride;
+            if (rowcompute) face_modes(smem_raw, fA, uA);
             if (FLAGS) {
                 __syncwarp();
                 if (tx == 0) mbar_arrive(&ebars[0]);
             }
         }
 
-        // ---- march: step t handles element layer e = pfirst + t, upper plane pfirst + t + 1 -----
-        const int nsteps = z1 - pfirst;
-        if (!FLAGS || ty < TY - 1)
-        for (int t = 0; t < nsteps; t++) {
+        // ---- one z-step: element layer e = pfirst + t, upper plane pfirst + t + 1 ---------------
+        // fl/uo/mo: lower-face modes, own nodal value and mask of plane e (from the previous step);
+        // fn/un/mn: the same for plane e + 1 (for the next step)
+        auto step = [&](const int t, const double (&fl)[12], double (&fn)[12], const double (&uo)[3], double (&un)[3],
+                        const unsigned mo, unsigned& mn) {
             const int pidx = t + 1;
             const int s = pidx % L::STAGES;
             const unsigned char* st = smem_raw + s * L::STAGE_BYTES;
-            const unsigned mnew = load_mask(pfirst + pidx);  // consumed one step later
+            mn = (innode && pfirst + pidx < P.nzl) ? (unsigned)*mptr : 0u;  // consumed one step later
+            mptr += P.mstride;
+            double* xw = xch + (t % L::XCH_DEPTH) * 6 * NT;
+            if (!FLAGS && !rowcompute) {  // idle top row of the barrier variant
+                mbar_wait(&bars[s], (pidx / L::STAGES) & 1);
+                __syncthreads();
+                return;
+            }
             mbar_wait(&bars[s], (pidx / L::STAGES) & 1);
-
-#ifndef TOB_KB_LDS
             // Block constants straight from the kernel-parameter constant bank as uniform-register operands of the
-            // DP instructions (SASS: LDCU.64 c[0x0][UR+imm] ... DFMA R, R, UR, R).  The index carries a term that is
+            // DP instructions (SASS: LDCU.128 c[0x0][UR+imm] ... DFMA R, R, UR, R).  The index carries a term that is
             // zero for every reachable t but opaque to ptxas: with a loop-invariant address it hoists all 48 loads
             // and then thrashes the 63 uniform registers (R2UR spills); re-loading per step keeps the shared-memory
-            // pipe (the co-limiting unit next to FP64: 24 of ~95 wavefronts per warp-step were these constants)
-            // and 12 vector registers free.
-            const double* kz = &KB.b[0][0] + (t >> 30);
-#endif
+            // pipe (24 of ~95 wavefronts per warp-step were these constants) and 12 vector registers free.
+            const double2* kz = &KB.k[0][0] + (t >> 30);
+
             double ex0[3][2];  // edge (row j) contributions of my face
-            double unew[3] = {0.0, 0.0, 0.0};
-            double* xw = xch + (t % L::XCH_DEPTH) * 6 * NT;
-            if (compute) {
-                double fnew[3][4];
-                face_modes(st, fnew, unew);
+            {
+                face_modes(st, fn, un);
                 const double Ee = reinterpret_cast<const double*>(st + L::U_BYTES)[o];
                 // Z stage: element modes  uh[c][ma + 2 mb + 4 mg]
                 double uh[3][8];
@@ -417,26 +401,16 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                 for (int c = 0; c < 3; c++)
 #pragma unroll
                     for (int f = 0; f < 4; f++) {
-                        const double fl = SMEM_STATE ? fps[(4 * c + f) * NT] : fpr[4 * c + f];
-                        uh[c][f] = fl + fnew[c][f];
-                        uh[c][4 + f] = fl - fnew[c][f];
-                        if (SMEM_STATE) fps[(4 * c + f) * NT] = fnew[c][f];
-                        else fpr[4 * c + f] = fnew[c][f];
+                        uh[c][f] = fl[4 * c + f] + fn[4 * c + f];
+                        uh[c][4 + f] = fl[4 * c + f] - fn[4 * c + f];
                     }
-                // 8 symmetric blocks of 3x3, scaled by the modulus (rho = 1,2,4 have a zero row/column)
+                // 8 symmetric blocks of 3x3 (rho = 1,2,4 have a zero row/column)
                 double yh[3][8];
 #pragma unroll
                 for (int rho = 0; rho < 8; rho++) {
                     const double in0 = uh[0][rho ^ 1], in1 = uh[1][rho ^ 2], in2 = uh[2][rho ^ 4];
-                    double b00, b01, b02, b11, b12, b22;
-#ifdef TOB_KB_LDS
-                    lds2(b00, b01, kb_addr + rho * 48);
-                    lds2(b02, b11, kb_addr + rho * 48 + 16);
-                    lds2(b12, b22, kb_addr + rho * 48 + 32);
-#else
-                    b00 = kz[rho * 9 + 0]; b01 = kz[rho * 9 + 1]; b02 = kz[rho * 9 + 2];
-                    b11 = kz[rho * 9 + 4]; b12 = kz[rho * 9 + 5]; b22 = kz[rho * 9 + 8];
-#endif
+                    const double2 k0 = kz[rho * 3 + 0], k1 = kz[rho * 3 + 1], k2 = kz[rho * 3 + 2];
+                    const double b00 = k0.x, b01 = k0.y, b02 = k1.x, b11 = k1.y, b12 = k2.x, b22 = k2.y;
                     double o0, o1, o2;
                     if (rho == 1) {
                         o0 = 0.0;
@@ -466,9 +440,8 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 #pragma unroll
                     for (int f = 0; f < 4; f++) {
                         const double sl = yh[c][f] + yh[c][4 + f], su2 = yh[c][f] - yh[c][4 + f];
-                        ht[c][f] = fma(Ee, sl, SMEM_STATE ? ups[(4 * c + f) * NT] : upr[4 * c + f]);
-                        if (SMEM_STATE) ups[(4 * c + f) * NT] = Ee * su2;
-                        else upr[4 * c + f] = Ee * su2;
+                        ht[c][f] = fma(Ee, sl, upr[4 * c + f]);
+                        upr[4 * c + f] = Ee * su2;
                     }
                 // Y' stage: row j part stays, row j+1 part goes to the thread above
 #pragma unroll
@@ -478,9 +451,6 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         ex0[c][ma] = ht[c][ma] + ht[c][ma + 2];
                         xw[(2 * c + ma) * NT + o2] = ht[c][ma] - ht[c][ma + 2];
                     }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; c++) { ex0[c][0] = 0.0; ex0[c][1] = 0.0; }
             }
             if (FLAGS) {
                 __syncwarp();
@@ -509,17 +479,17 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 
             const int e = pfirst + t;  // node plane completed by this step
             if (outthr && e >= z0) {
+                const long long idx0 = e * P.pstride + (long long)j * P.px + i;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    const long long idx = e * P.pstride + c * P.nstride + (long long)j * P.px + i;
-                    const bool fixed = (mown >> c) & 1u;
-                    const double uo = uown[c];  // own nodal value on plane e
-                    const double au = fixed ? uo : v[c];
+                    const long long idx = idx0 + c * P.nstride;
+                    const bool fixed = (mo >> c) & 1u;
+                    const double au = fixed ? uo[c] : v[c];
                     if (EPI == EPI_Y) {
                         P.y[idx] = au;
                     } else if (EPI == EPI_DOT) {
                         P.y[idx] = au;
-                        part = fma(uo, au, part);
+                        part = fma(uo[c], au, part);
                     } else if (EPI == EPI_RESID) {
                         const double r = P.a0[idx] - au;
                         P.y[idx] = r;
@@ -528,16 +498,26 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         const double r = P.a0[idx] - au;
                         const double dn = P.s0 * P.o1[idx] + P.s1 * P.a1[idx] * r;
                         P.o1[idx] = dn;
-                        P.y[idx] = uo + dn;
+                        P.y[idx] = uo[c] + dn;
                     }
                 }
             }
-            mown = mnew;
-#pragma unroll
-            for (int c = 0; c < 3; c++) uown[c] = unew[c];
             if (FLAGS) {  // this row is done with plane pidx and with the exchange slot of step t
                 __syncwarp();
                 if (tx == 0) mbar_arrive(&ebars[pidx % L::STAGES]);
+            }
+        };
+
+        // ---- march -------------------------------------------------------------------------------
+        const int nsteps = z1 - pfirst;
+        if (!FLAGS || rowcompute) {
+            for (int t = 0; t < nsteps; t++) {
+                step(t, fA, fB, uA, uB, mA, mB);
+#pragma unroll
+                for (int k = 0; k < 12; k++) fA[k] = fB[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) uA[k] = uB[k];
+                mA = mB;
             }
         }
     }
@@ -564,9 +544,9 @@ static int encode_map(tob_ctx_impl* c, CUtensorMap* tm, CUtensorMapDataType dt, 
     return 0;
 }
 
-template <int TY, int EPI, bool SMEM_STATE, bool FLAGS>
+template <int TY, int EPI, bool FLAGS>
 static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
-    using L = ZmSmem<TY, SMEM_STATE, FLAGS>;
+    using L = ZmSmem<TY, FLAGS>;
     CUtensorMap tmU, tmE;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, 3, (cuuint64_t)g.nzl()};
@@ -606,26 +586,33 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
     if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
-    auto kern = k_hex8_zmarch<TY, EPI, SMEM_STATE, FLAGS>;
+    auto kern = k_hex8_zmarch<TY, EPI, FLAGS>;
     static bool attr_set = false;
     if (!attr_set) {
         TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, op.blocks, P);
+    Hex8BlocksPacked kp;
+    for (int rho = 0; rho < 8; rho++) {
+        const double* b = op.blocks.b[rho];
+        kp.k[rho][0] = make_double2(b[0], b[1]);
+        kp.k[rho][1] = make_double2(b[2], b[4]);
+        kp.k[rho][2] = make_double2(b[5], b[8]);
+    }
+    kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, kp, P);
     c->launches++;
     TOB_KERNEL_CHECK();
     if (nparts) *nparts = (EPI == EPI_DOT || EPI == EPI_RESID) ? gx * gy * nch : 0;
     return 0;
 }
 
-template <int TY, bool SMEM_STATE, bool FLAGS>
+template <int TY, bool FLAGS>
 static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     switch (a.epi) {
-        case EPI_Y: return launch_zm<TY, EPI_Y, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
-        case EPI_DOT: return launch_zm<TY, EPI_DOT, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
-        case EPI_RESID: return launch_zm<TY, EPI_RESID, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
-        default: return launch_zm<TY, EPI_CHEB, SMEM_STATE, FLAGS>(c, g, op, a, nparts);
+        case EPI_Y: return launch_zm<TY, EPI_Y, FLAGS>(c, g, op, a, nparts);
+        case EPI_DOT: return launch_zm<TY, EPI_DOT, FLAGS>(c, g, op, a, nparts);
+        case EPI_RESID: return launch_zm<TY, EPI_RESID, FLAGS>(c, g, op, a, nparts);
+        default: return launch_zm<TY, EPI_CHEB, FLAGS>(c, g, op, a, nparts);
     }
 }
 
@@ -645,14 +632,14 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
         TOB_KERNEL_CHECK();
         return 0;
     }
-    if (kernel == SPMV_ZM16) return dispatch_zm<16, true, false>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM12) return dispatch_zm<12, false, false>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM8R) return dispatch_zm<8, false, false>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM8RF) return dispatch_zm<8, false, true>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM16RF) return dispatch_zm<16, false, true>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM12RF) return dispatch_zm<12, false, true>(c, g, op, a, nparts);
-    if (kernel == SPMV_ZM16R) return dispatch_zm<16, false, false>(c, g, op, a, nparts);
-    return dispatch_zm<8, true, false>(c, g, op, a, nparts);
+    // (the shared-memory-state variants SPMV_ZM8 / SPMV_ZM16 of the first kernel generation are retired: their ids
+    // run the register-state kernels of the same tile shape)
+    if (kernel == SPMV_ZM16 || kernel == SPMV_ZM16R) return dispatch_zm<16, false>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM12) return dispatch_zm<12, false>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM8RF) return dispatch_zm<8, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16RF) return dispatch_zm<16, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM12RF) return dispatch_zm<12, true>(c, g, op, a, nparts);
+    return dispatch_zm<8, false>(c, g, op, a, nparts);  // SPMV_ZM8, SPMV_ZM8R
 }
 
 // ---------------------------------------------------------------------------------------
