@@ -51,6 +51,11 @@ def test_own_driver_matches_oracle(oracle, tmp_path):
     names = len(b"ux, uy, uz\x01") + len(b"x, xTilde, xPhys\x01")
     expect = 26 + 48 + names + npts * 12 + ncells * 80 + ndumps * (8 + 4 * 3 * npts + 4 * 3 * ncells)
     assert len(data) == expect
+    pts, conn, offs, typ, dumps = parse_container(tmp_path / "output_00000.dat")
+    assert [d[0] for d in dumps] == [1, 2, 3, 4, 4] or len(dumps) == 5
+    assert conn.max() == npts - 1 and int(offs[-1]) == 8 * ncells and set(typ.tolist()) == {12}
+    assert abs(float(pts[:, 0].max()) - 2.0) < 1e-6 and abs(float(pts[:, 2].max()) - 1.0) < 1e-6
+    assert 0.0 <= float(dumps[-1][2][2].min()) and float(dumps[-1][2][2].max()) <= 1.0  # xPhys in [0,1]
 
 
 def test_untouched_main_and_mma_dropin(tmp_path):
@@ -80,13 +85,51 @@ def test_restart_roundtrip(tmp_path):
     assert np.abs(cont[:, 1] - full[10:, 1]).max() <= 1e-4 * full[10, 1]
 
 
+def parse_container(path, npf=3, ncf=3):
+    """Reader for the result container (the layout the reference's bin2vtu_v3.py:23-144 expects)."""
+    import struct
+    data = open(path, "rb").read()
+    pos = data.index(b"\x01") + 1
+    nd, npts, ncells, a, b, npe = struct.unpack("6Q", data[pos:pos + 48])
+    assert (nd, a, b, npe) == (1, npf, ncf, 8)
+    pos += 48
+    for _ in range(2):
+        pos = data.index(b"\x01", pos) + 1
+    pts = np.frombuffer(data, dtype=np.float32, count=3 * npts, offset=pos).reshape(npts, 3); pos += 12 * npts
+    conn = np.frombuffer(data[pos:pos + 64 * ncells], dtype=np.uint64).reshape(ncells, 8); pos += 64 * ncells
+    offs = np.frombuffer(data[pos:pos + 8 * ncells], dtype=np.uint64); pos += 8 * ncells
+    typ = np.frombuffer(data[pos:pos + 8 * ncells], dtype=np.uint64); pos += 8 * ncells
+    dumps = []
+    while pos < len(data):
+        itr = struct.unpack("Q", data[pos:pos + 8])[0]; pos += 8
+        pf = np.frombuffer(data[pos:pos + 4 * npf * npts], dtype=np.float32).reshape(npf, npts); pos += 4 * npf * npts
+        cf = np.frombuffer(data[pos:pos + 4 * ncf * ncells], dtype=np.float32).reshape(ncf, ncells); pos += 4 * ncf * ncells
+        dumps.append((itr, pf, cf))
+    assert pos == len(data)
+    return pts, conn, offs, typ, dumps
+
+
 def test_two_rank_run_matches_single(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     args = ["-nx", "17", "-ny", "9", "-nz", "17", "-nlvls", "1", "-rmin", "0.3", "-maxItr", "3", "-tob_rtol", "1e-11",
-            "-tob_maxits", "50000", "-restart", "0", "-tob_output", "0"]
-    one = history(run([DRIVER] + args, tmp_path))
-    two = history(run([TOBRUN, "-np", "2", DRIVER] + args, tmp_path))
+            "-tob_maxits", "50000", "-restart", "0"]
+    d1, d2 = tmp_path / "one", tmp_path / "two"
+    d1.mkdir(); d2.mkdir()
+    one = history(run([DRIVER] + args, d1))
+    two = history(run([TOBRUN, "-np", "2", DRIVER] + args, d2))
     assert one.shape == two.shape == (3, 6)
     assert np.abs(one - two).max() <= 2e-6
+    # every rank writes its slab of the result container at the global offsets: the 2-rank file has the same mesh
+    # (bit-identical) and the same fields (fp32 casts of values that agree to solver tolerance) as the 1-rank file
+    a = parse_container(d1 / "output_00000.dat")
+    b = parse_container(d2 / "output_00000.dat")
+    assert len(a[0]) == 17 * 9 * 17 and len(a[1]) == 16 * 8 * 16
+    for k in range(4):
+        assert np.array_equal(a[k], b[k])
+    assert len(a[4]) == len(b[4]) == 4  # iterations 1..3 and the final dump
+    for (ia, pa, ca), (ib, pb, cb) in zip(a[4], b[4]):
+        assert ia == ib
+        assert np.abs(pa - pb).max() <= 1e-5 * max(1.0, np.abs(pa).max())
+        assert np.abs(ca - cb).max() <= 1e-5

@@ -1,5 +1,6 @@
-// MPIIO.h -- class surface of the reference's result writer (MPIIO.h:34-89).  Single-writer restatement of
-// the output_00000.dat container: readable by the reference's bin2vtu_v3.py.
+// MPIIO.h -- class surface of the reference's result writer (MPIIO.h:34-89).  Restatement of the
+// output_00000.dat container, readable by the reference's bin2vtu_v3.py; every rank writes its
+// own z-slab at the offsets the reference's collective MPI-IO write would use.
 #ifndef TOB_MPIIO_H
 #define TOB_MPIIO_H
 #include <string>
@@ -13,8 +14,12 @@ class MPIIO {
 
   private:
     std::string filename;
-    unsigned long nPoints, nCells;
+    unsigned long nPoints, nCells;  // owned by this rank
     int nPF, nCF;
     bool enabled;
+    unsigned long p0, c0;              // global index of my first point / cell
+    unsigned long nPointsG, nCellsG;   // whole grid
+    unsigned long data0;               // file offset of the first dump
+    unsigned long ndumps;
 };
 #endif
