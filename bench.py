@@ -202,10 +202,11 @@ def run_ours(args):
         return float(ms.item()), clocks, loop.pcg_its[nwarm:]
 
     K, W = args.steps, args.warmup
-    # deepest hierarchy (<= 6 levels) whose coarsening divides the grid and keeps the z-slab boundaries aligned
+    # deepest hierarchy (<= 6 levels) whose coarsening divides the grid; on N > 1 ranks the levels whose slab
+    # boundaries are no longer aligned (or that are small) are replicated on every rank, so the depth does not depend on N
     # (profiles/r01_gmg_sweep_192x96x96.txt: 6 levels + 20 coarse iterations beat 4 levels + 60 by 2-3x)
     nlv = 6
-    while nlv > 2 and any(d % (1 << (nlv - 1)) for d in (c["nex"], c["ney"], c["nez"], c["nez"] // world)):
+    while nlv > 2 and any(d % (1 << (nlv - 1)) for d in (c["nex"], c["ney"], c["nez"])):
         nlv -= 1
     main_pc = 1 if args.solver == "gmg" else 0
     # ---- device-resident arm -----------------------------------------------------------------
@@ -223,7 +224,7 @@ def run_ours(args):
 
     # ---- same job with the multigrid-preconditioned solver (not the BASELINE-named cfg2 solver; reported beside it) ----
     gmg = None
-    if (c["nez"] // world) % (1 << (nlv - 1)) == 0 and not args.no_gmg and main_pc == 0:
+    if not args.no_gmg and main_pc == 0:
         loop3 = DesignLoop(ctx, resident=True, pc=1, nlvls=nlv)
         ms3, _, its3 = timed(loop3, K, W)
         gmg = {"value": K / (ms3 * 1e-3), "unit": "design iterations/s (whole job)", "ms_per_step": ms3 / K, "nlvls": nlv,

@@ -198,7 +198,7 @@ void peer_teardown(tob_ctx_impl* c) {
 
 // ---- halo exchange of nodal planes -------------------------------------------------------------------------
 int halo_nodes(tob_ctx_impl* c, const LevelGrid& g, double* v) {
-    if (c->desc.nranks == 1) return 0;
+    if (c->desc.nranks == 1 || g.replicated) return 0;
     const int r = c->desc.rank, n = c->desc.nranks;
     const size_t cnt = (size_t)g.pstride;
     PeerComm& pc = c->peer;
@@ -242,6 +242,23 @@ int halo_elems(tob_ctx_impl* c, double* v, long long layer_stride, int own0, int
     if (r < n - 1) {
         if (send_up) TOB_NCCL(ncclSend(v + (long long)(own1 - send_up) * layer_stride, (size_t)send_up * layer_stride, ncclDouble, r + 1, c->comm, c->stream));
         if (recv_hi) TOB_NCCL(ncclRecv(v + (long long)own1 * layer_stride, (size_t)recv_hi * layer_stride, ncclDouble, r + 1, c->comm, c->stream));
+    }
+    TOB_NCCL(ncclGroupEnd());
+    return 0;
+}
+
+// all-gather of one contiguous chunk per rank (different sizes): rank k's chunk lands at dst + off[k] on every rank
+// (set-up traffic and the once-per-V-cycle gather of the coarse residual; NCCL is graph-capturable)
+int allgatherv_bytes(tob_ctx_impl* c, const void* mine, void* dst, const size_t* off, const size_t* cnt) {
+    const int n = c->desc.nranks, r = c->desc.rank;
+    if (n == 1) {
+        if (cnt[0]) TOB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off[0], mine, cnt[0], cudaMemcpyDeviceToDevice, c->stream));
+        return 0;
+    }
+    TOB_NCCL(ncclGroupStart());
+    for (int k = 0; k < n; k++) {
+        char* recv = static_cast<char*>(dst) + off[k];
+        TOB_NCCL(ncclBroadcast(k == r ? mine : static_cast<const void*>(recv), recv, cnt[k], ncclChar, k, c->comm, c->stream));
     }
     TOB_NCCL(ncclGroupEnd());
     return 0;

@@ -67,6 +67,9 @@ struct LevelGrid {
     long long evec = 0;             // doubles in a stored element field
     long long own_off = 0, own_len = 0;  // contiguous owned range of a nodal vector
     double dx = 0, dy = 0, dz = 0;
+    // replicated: every rank holds the WHOLE grid of this (coarse multigrid) level and works on it redundantly --
+    // no halo exchange, no all-reduce (gmg.cu)
+    bool replicated = false;
     int nzl() const { return gn1 - gn0; }
     int nzle() const { return ge1 - ge0; }
     int zl_own0() const { return kn0 - gn0; }  // local index of first owned node plane
@@ -144,6 +147,7 @@ int halo_elems(tob_ctx_impl* c, double* v, long long layer_stride, int own0, int
 int peer_setup(tob_ctx_impl* c, size_t plane_bytes);
 void peer_teardown(tob_ctx_impl* c);
 int finalize_allreduce(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, int op);  // -1 = not available
+int allgatherv_bytes(tob_ctx_impl* c, const void* mine, void* dst, const size_t* off, const size_t* cnt);
 int allreduce_sum(tob_ctx_impl* c, double* d_vals, int n);
 int allreduce_max(tob_ctx_impl* c, double* d_vals, int n);
 

@@ -11,7 +11,12 @@
 //     lambda_max(D^-1 A) <= lambda_max(diag(KE)^-1 KE) for ANY modulus field (element-wise Rayleigh bound);
 //   * transfers are trilinear (Q1) prolongation per component and its transpose, as the reference's DMDA
 //     interpolation; Dirichlet dofs are injected to the coarse levels;
-//   * coarsest level: a fixed number of Jacobi-PCG iterations driven entirely by device scalars (no host sync).
+//   * coarsest level: a fixed number of Jacobi-PCG iterations driven entirely by device scalars (no host sync);
+//   * multi-GPU: the fine levels are z-slab distributed (halo planes over the NVLink arena); below a size threshold
+//     (or where the slab boundaries stop being aligned) the levels are REPLICATED: the restricted residual of the
+//     last distributed level is all-gathered once per V-cycle and every rank continues the cycle redundantly on the
+//     whole coarse grid -- no halo, no all-reduce, and as many levels as the global grid allows.  Coarse levels are
+//     launch-latency bound, so redundant work costs nothing while every exchange on them costs a latency.
 #include "elast.cuh"
 #include "vecops.cuh"
 
@@ -24,12 +29,17 @@ struct GmgLevel {
     double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *dinv = nullptr, *E = nullptr;
     unsigned char* mask = nullptr;
     bool own_E = false;
+    int res = 0;  // resolution index: this level's elements are 2^res fine elements wide
 };
 
 struct GmgHierarchy {
     std::vector<GmgLevel> lv;
     double lam_max = 2.0;   // bound on lambda_max(D^-1 A)
     double lam_ratio = 8.0; // Chebyshev targets [lam_max/ratio, lam_max]
+    // lv[0..dI] are distributed; if dI >= 0, lv[dI+1] is the replicated twin of lv[dI] (same resolution) and the
+    // levels after it are replicated too.  dI = -1: single rank, plain hierarchy.
+    int dI = -1;
+    std::vector<size_t> gn_off, gn_cnt, ge_off, ge_cnt, gm_off, gm_cnt;  // per-rank chunks of the gather (bytes)
     // coarsest-level PCG vectors
     double *cp = nullptr, *cq = nullptr;
     // CUDA graph of one V-cycle
@@ -222,7 +232,7 @@ static int coarse_solve(tob_elast_impl* h, GmgLevel& L, int its) {
         SpmvArgs a;
         a.u = mg->cp; a.y = mg->cq; a.epi = EPI_DOT;
         TOB_CHECK(level_apply(h, L, a, &np));
-        TOB_CHECK(finalize_sum(c, np, 1, G_S_PQ, true));
+        TOB_CHECK(finalize_sum(c, np, 1, G_S_PQ, !g.replicated));
         TOB_CHECK(pcg_update_xr(c, g, L.x, L.r, mg->cp, mg->cq, L.dinv, cur + 1, G_S_PQ, nxt));
         TOB_CHECK(pcg_update_p(c, g, mg->cp, L.r, L.dinv, nxt + 1, cur + 1, 0));
         int t = cur; cur = nxt; nxt = t;
@@ -235,6 +245,13 @@ static int vcycle(tob_elast_impl* h, int l) {
     GmgHierarchy* mg = h->mg;
     GmgLevel& L = mg->lv[l];
     const int nl = (int)mg->lv.size();
+    if (l == mg->dI) {
+        // last distributed level: hand the problem to its replicated twin and take back my slab of the answer
+        GmgLevel& R = mg->lv[l + 1];
+        TOB_CHECK(allgatherv_bytes(c, L.b + L.g.own_off, R.b, mg->gn_off.data(), mg->gn_cnt.data()));
+        TOB_CHECK(vcycle(h, l + 1));
+        return vec_copy(c, L.x, R.x + (long long)L.g.gn0 * L.g.pstride, L.g.nvec);  // stored planes incl. ghosts
+    }
     if (l == nl - 1) return coarse_solve(h, L, h->opts.coarse_its);
     const int k = h->opts.cheb_degree;
     TOB_CHECK(cheb_smooth(h, L, k, true));
@@ -256,8 +273,8 @@ static int vcycle(tob_elast_impl* h, int l) {
         TOB_KERNEL_CHECK();
     }
     TOB_CHECK(vcycle(h, l + 1));
-    // prolong and correct
-    TOB_CHECK(halo_nodes(c, C.g, C.x));
+    // prolong and correct (the gather level already holds its ghost planes)
+    if (l + 1 != mg->dI) TOB_CHECK(halo_nodes(c, C.g, C.x));
     {
         const LevelGrid &f = L.g, &g = C.g;
         dim3 grid(div_up(f.nxn, 128), f.nyn, f.zl_own1() - f.zl_own0());
@@ -324,29 +341,59 @@ int gmg_update(tob_elast_impl* h) {
     for (size_t l = 1; l < mg->lv.size(); l++) {
         GmgLevel &F = mg->lv[l - 1], &C = mg->lv[l];
         const LevelGrid &f = F.g, &g = C.g;
+        if ((int)l == mg->dI + 1) {
+            // replicated twin of the last distributed level: gather the owned element layers of every rank
+            TOB_CHECK(allgatherv_bytes(c, F.E + (long long)(f.ke0 - f.ge0) * f.estride, C.E, mg->ge_off.data(), mg->ge_cnt.data()));
+            TOB_CHECK(hex8_diag_inv(c, g, C.op, C.E, C.mask, C.dinv, true));
+            continue;
+        }
         const int nlc = g.ke1 - g.ke0;
         dim3 grid(div_up(g.nex, 128), g.ney, nlc);
         k_coarsen_E<<<grid, 128, 0, c->stream>>>(F.E, C.E, g.nex, g.ney, f.pe, g.pe, f.estride, g.estride, f.ke0 - f.ge0,
                                                  g.ke0 - g.ge0, nlc);
         c->launches++;
         TOB_KERNEL_CHECK();
-        const int own0 = g.ke0 - g.ge0, own1 = g.ke1 - g.ge0;
-        TOB_CHECK(halo_elems(c, C.E, g.estride, own0, own1, 0, g.nzle() - own1, c->desc.rank > 0 ? 1 : 0, 0));
+        if (!g.replicated) {
+            const int own0 = g.ke0 - g.ge0, own1 = g.ke1 - g.ge0;
+            TOB_CHECK(halo_elems(c, C.E, g.estride, own0, own1, 0, g.nzle() - own1, c->desc.rank > 0 ? 1 : 0, 0));
+        }
         TOB_CHECK(hex8_diag_inv(c, g, C.op, C.E, C.mask, C.dinv, true));
     }
     return 0;
 }
 
+// levels below this many elements are replicated on every rank instead of z-slab distributed
+constexpr long long kReplicateBelowElems = 300000;
+
 int gmg_setup(tob_elast_impl* h) {
     tob_ctx_impl* c = h->c;
     if (h->mg) return 0;
     const LevelGrid& g0 = *h->g;
-    const int nl = h->opts.nlvls;
-    if (nl < 2) TOB_FAIL("multigrid needs nlvls >= 2");
-    const int div = 1 << (nl - 1);
+    const int nres = h->opts.nlvls;
+    if (nres < 2) TOB_FAIL("multigrid needs nlvls >= 2");
+    const int div = 1 << (nres - 1);
     if (g0.nex % div || g0.ney % div || g0.nez % div) TOB_FAIL("MESH DIMENSION NOT COMPATIBLE WITH NUMBER OF MULTIGRID LEVELS (TopOpt.cc:182-201)");
-    if ((g0.ke0 % div) || (g0.ke1 % div)) TOB_FAIL("z-slab boundaries must be multiples of 2^(nlvls-1) element layers");
+    const int nranks = c->desc.nranks, rank = c->desc.rank;
     auto* mg = new GmgHierarchy();
+    // where the hierarchy switches from distributed to replicated levels (the same decision on every rank: it only
+    // depends on the ownership rule, not on communicated data)
+    int dI = -1;
+    std::vector<int> rk0(nranks), rk1(nranks);
+    if (nranks > 1) {
+        int aligned = nres - 1;  // deepest resolution index at which every slab boundary is still a coarse element boundary
+        for (int r = 0; r < nranks; r++) {
+            TOB_CHECK(tob_slab_partition(g0.nzn, nranks, r, nullptr, nullptr, &rk0[r], &rk1[r]));
+            for (int l = 0; l <= aligned; l++)
+                if ((rk0[r] % (1 << l)) || (rk1[r] % (1 << l))) { aligned = l - 1; break; }
+        }
+        int small = nres - 1;  // first resolution (>= 1) with fewer elements than the threshold
+        for (int l = 1; l < nres; l++)
+            if (((long long)(g0.nex >> l) * (g0.ney >> l) * (g0.nez >> l)) < kReplicateBelowElems) { small = l; break; }
+        dI = std::min(aligned, small);
+    }
+    mg->dI = dI;
+    const int ndist = dI >= 0 ? dI + 1 : nres;       // distributed levels (single rank: all of them)
+    const int nl = dI >= 0 ? ndist + (nres - dI) : nres;
     mg->lv.resize(nl);
     mg->lam_max = element_rayleigh_bound(h->op.KE);
     GmgLevel& L0 = mg->lv[0];
@@ -356,11 +403,19 @@ int gmg_setup(tob_elast_impl* h) {
     for (int l = 0; l < nl; l++) {
         GmgLevel& L = mg->lv[l];
         if (l > 0) {
-            const LevelGrid& f = mg->lv[l - 1].g;
-            const int rank = c->desc.rank;
-            const int ke0 = f.ke0 / 2, ke1 = f.ke1 / 2;
-            const int kn0 = rank == 0 ? 0 : ke0 + 1, kn1 = ke1 + 1;
-            make_level_grid(L.g, f.nex / 2 + 1, f.ney / 2 + 1, f.nez / 2 + 1, 2 * f.dx, 2 * f.dy, 2 * f.dz, rank, c->desc.nranks, kn0, kn1);
+            if (l < ndist) {  // distributed, coarsened from the level above
+                const LevelGrid& f = mg->lv[l - 1].g;
+                const int ke0 = f.ke0 / 2, ke1 = f.ke1 / 2;
+                const int kn0 = rank == 0 ? 0 : ke0 + 1, kn1 = ke1 + 1;
+                L.res = l;
+                make_level_grid(L.g, f.nex / 2 + 1, f.ney / 2 + 1, f.nez / 2 + 1, 2 * f.dx, 2 * f.dy, 2 * f.dz, rank, nranks, kn0, kn1);
+            } else {  // replicated: the whole grid of resolution res on every rank
+                L.res = dI + (l - ndist);
+                const int sc = 1 << L.res;
+                const int nzn = g0.nez / sc + 1;
+                make_level_grid(L.g, g0.nex / sc + 1, g0.ney / sc + 1, nzn, sc * g0.dx, sc * g0.dy, sc * g0.dz, 0, 1, 0, nzn);
+                L.g.replicated = true;
+            }
             TOB_CHECK(hex8_build_operator(L.g.dx, L.g.dy, L.g.dz, h->nu, L.op));
             L.own_op = true;
             TOB_CHECK(galloc(c, &L.E, L.g.evec));
@@ -371,6 +426,20 @@ int gmg_setup(tob_elast_impl* h) {
         }
         double** vs[] = {&L.x, &L.x2, &L.b, &L.r, &L.d};
         for (auto v : vs) TOB_CHECK(galloc(c, v, L.g.nvec));
+    }
+    if (dI >= 0) {  // chunks of the gather from lv[dI] (distributed) to lv[dI+1] (replicated, same pitches)
+        const LevelGrid& d = mg->lv[dI].g;
+        const LevelGrid& t = mg->lv[dI + 1].g;
+        if (d.pstride != t.pstride || d.estride != t.estride || d.mstride != t.mstride) TOB_FAIL("internal: gather level pitches differ");
+        mg->gn_off.resize(nranks); mg->gn_cnt.resize(nranks); mg->ge_off.resize(nranks); mg->ge_cnt.resize(nranks);
+        mg->gm_off.resize(nranks); mg->gm_cnt.resize(nranks);
+        for (int r = 0; r < nranks; r++) {
+            const int ke0 = rk0[r] >> dI, ke1 = rk1[r] >> dI;
+            const int kn0 = r == 0 ? 0 : ke0 + 1, kn1 = ke1 + 1;
+            mg->gn_off[r] = (size_t)kn0 * d.pstride * 8; mg->gn_cnt[r] = (size_t)(kn1 - kn0) * d.pstride * 8;
+            mg->ge_off[r] = (size_t)ke0 * d.estride * 8; mg->ge_cnt[r] = (size_t)(ke1 - ke0) * d.estride * 8;
+            mg->gm_off[r] = (size_t)kn0 * d.mstride;     mg->gm_cnt[r] = (size_t)(kn1 - kn0) * d.mstride;
+        }
     }
     TOB_CHECK(galloc(c, &mg->cp, mg->lv[nl - 1].g.nvec));
     TOB_CHECK(galloc(c, &mg->cq, mg->lv[nl - 1].g.nvec));
@@ -389,6 +458,10 @@ int gmg_refresh_masks(tob_elast_impl* h) {
     for (size_t l = 1; l < mg->lv.size(); l++) {
         GmgLevel &F = mg->lv[l - 1], &C = mg->lv[l];
         const LevelGrid &f = F.g, &g = C.g;
+        if ((int)l == mg->dI + 1) {  // replicated twin: gather the owned mask planes of every rank
+            TOB_CHECK(allgatherv_bytes(c, F.mask + (long long)f.zl_own0() * f.mstride, C.mask, mg->gm_off.data(), mg->gm_cnt.data()));
+            continue;
+        }
         // local coarse plane kc <-> global 2*(kc+gc0) -> local fine 2*(kc+gc0)-gf0 ; handle via offset arithmetic
         for (int kc = 0; kc < g.nzl(); kc++) {
             const int kf = 2 * (kc + g.gn0) - f.gn0;

@@ -243,7 +243,7 @@ int pcg_update_xr(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, con
                                                       s_num, s_den, c->d_partials);
     c->launches++;
     TOB_KERNEL_CHECK();
-    return finalize_sum(c, nb, 2, slot_rr_rz, true);
+    return finalize_sum(c, nb, 2, slot_rr_rz, !g.replicated);
 }
 int pcg_update_p(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* z_or_r, const double* dinv, int s_num,
                  int s_den, int first) {
