@@ -225,13 +225,16 @@ def run_ours(args):
     # ---- same job with the multigrid-preconditioned solver (not the BASELINE-named cfg2 solver; reported beside it) ----
     gmg = None
     if not args.no_gmg and main_pc == 0:
-        loop3 = DesignLoop(ctx, resident=True, pc=1, nlvls=nlv)
-        ms3, _, its3 = timed(loop3, K, W)
-        gmg = {"value": K / (ms3 * 1e-3), "unit": "design iterations/s (whole job)", "ms_per_step": ms3 / K, "nlvls": nlv,
-               "pcg_iterations_per_step": its3, "smoother": "Chebyshev-Jacobi degree 3",
-               "coarse": f"{20 if nlv >= 5 else 60} Jacobi-PCG iterations",
-               "final_fx": loop3.hist[-1]["fx"]}
-        loop3.close()
+        try:  # a secondary leg must never take the headline measurement down with it
+            loop3 = DesignLoop(ctx, resident=True, pc=1, nlvls=nlv)
+            ms3, _, its3 = timed(loop3, K, W)
+            gmg = {"value": K / (ms3 * 1e-3), "unit": "design iterations/s (whole job)", "ms_per_step": ms3 / K, "nlvls": nlv,
+                   "pcg_iterations_per_step": its3, "smoother": "Chebyshev-Jacobi degree 3",
+                   "coarse": f"{20 if nlv >= 5 else 60} Jacobi-PCG iterations",
+                   "final_fx": loop3.hist[-1]["fx"]}
+            loop3.close()
+        except Exception as e:  # noqa: BLE001
+            gmg = {"error": str(e)[:300]}
 
     if rank == 0:
         peak, kind = peaks()
