@@ -50,8 +50,10 @@ typedef struct tob_solver_opts {
     int check_every;     /* host convergence check cadence (iterations) */
     int cheb_degree;     /* Chebyshev-Jacobi smoothing steps per sweep (reference: GMRES(4)+SOR, 4 its) */
     int coarse_its;      /* coarse-grid PCG iteration cap (reference: GMRES(30)+SOR, 30 its) */
-    int spmv_kernel;     /* 0 = auto (z-march TY=8, register state), 1 = naive dense gather (cross-check), 2/3 = z-march TY=8/16 with
-                            shared-memory state, 4/5 = z-march TY=12/8 with register state */
+    int spmv_kernel;     /* 0 = auto (7).  1 = naive dense gather (cross-check).  z-march kernels, 32 x TY node columns per CTA,
+                            carried state in registers: 5 = TY 8, 9 = TY 16, 4 = TY 12 with one __syncthreads per z-step;
+                            6 / 7 / 8 = TY 8 / 16 / 12 with mbarrier row hand-off and a TMA producer warp.
+                            2 / 3 = retired shared-memory-state variants, run as 5 / 9. */
     int verbose;
 } tob_solver_opts;
 

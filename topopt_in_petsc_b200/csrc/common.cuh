@@ -115,6 +115,10 @@ struct tob_ctx_impl {
     double* h_scalars = nullptr;   // pinned mirror
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
+    // L2 eviction hints in the Jacobi-PCG kernels (env TOB_L2HINT, bit mask): 1 = once-per-iteration streams
+    // (x, r, dinv, E) evict_first, 2 = search direction p evict_last, 4 = q / r: stored with normal priority,
+    // evict_first at their last read
+    int l2hint = 0;
     DevBuf stage[8];  // staging buffers for host<->device vectors
     // TMA encode entry point
     void* encode_tiled = nullptr;
@@ -147,6 +151,32 @@ int halo_elems(tob_ctx_impl* c, double* v, long long layer_stride, int own0, int
 int peer_setup(tob_ctx_impl* c, size_t plane_bytes);
 void peer_teardown(tob_ctx_impl* c);
 int finalize_allreduce(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, int op);  // -1 = not available
+// L2 eviction-priority hints (createpolicy + .L2::cache_hint, sm_80+).  The Jacobi-PCG working set (6 vectors) is
+// twice the 126 MB L2 and every kernel walks its arrays front to back, so plain LRU evicts each line just before its
+// next use.  Marking the once-per-iteration streams evict_first lets the search direction p (read by all three kernels
+// of an iteration) and the freshly written q / r survive until their consumer runs (tob_ctx_impl::l2hint).
+__device__ __forceinline__ uint64_t l2_policy_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double2 ld2_hint(const double2* p, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st2_hint(double2* p, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st1_hint(double* p, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 int allgatherv_bytes(tob_ctx_impl* c, const void* mine, void* dst, const size_t* off, const size_t* cnt);
 int allreduce_sum(tob_ctx_impl* c, double* d_vals, int n);
 int allreduce_max(tob_ctx_impl* c, double* d_vals, int n);

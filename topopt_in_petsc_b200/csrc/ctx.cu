@@ -121,6 +121,7 @@ int tob_ctx_create(const tob_grid_desc* d, tob_ctx** out) {
     TOB_CUDA(cudaGetDeviceProperties(&prop, c->device));
     if (prop.major < 9) TOB_FAIL("libtopopt_b200 needs TMA/mbarrier hardware (built for sm_100a)");
     c->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("TOB_L2HINT")) c->l2hint = atoi(e);
     if (d->stream) { c->stream = (cudaStream_t)d->stream; c->own_stream = false; }
     else { TOB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     TOB_CUDA(cudaEventCreate(&c->ev0));

@@ -30,6 +30,8 @@ int elast_apply(tob_elast_impl* h, const double* u, double* y, int epi, bool mas
     }
     a.u = u; a.y = y; a.E = h->E_st; a.mask = h->mask; a.epi = epi; a.mask_in = mask_in;
     a.a0 = a0;
+    // Jacobi-PCG on one rank: working set >> L2, see common.cuh (the smaller per-rank sets of N > 1 mostly fit)
+    if (epi == EPI_DOT && h->opts.pc == 0 && h->c->desc.nranks == 1) a.l2hint = h->c->l2hint;
     h->stats.spmv_calls++;
     constexpr int kMaxPairs = 2048;
     // profiling mode 1 times every launch, mode >1 every mode-th launch (event pairs around every launch cost ~6 %

@@ -187,9 +187,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void lds2(double& a, double& b, uint32_t addr) {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
-}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -200,6 +197,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_hint(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                 uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
         : "memory");
 }
 
@@ -221,6 +232,7 @@ struct ZmParams {
     double* o1;
     double s0, s1;
     double* partials;
+    int l2hint;  // Jacobi-PCG only (common.cuh): 1 = modulus tiles evict_first, 2 = input vector (p) evict_last
 };
 
 // TMA tiles are ZM_W = 34 doubles wide: with a non-swizzled tensor map the innermost start
@@ -307,8 +319,10 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
             unsigned char* st = smem_raw + s * L::STAGE_BYTES;
             const int p = pfirst + pidx;
             mbar_expect_tx(&bars[s], L::TX_BYTES);
-            tma_load_4d(st, &tmU, &bars[s], i0 - 1, j0, 0, p);
-            tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
+            if (P.l2hint & 2) tma_load_4d_hint(st, &tmU, &bars[s], i0 - 1, j0, 0, p, l2_policy_last());
+            else tma_load_4d(st, &tmU, &bars[s], i0 - 1, j0, 0, p);
+            if (P.l2hint & 1) tma_load_3d_hint(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1, l2_policy_first());
+            else tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
         };
         if (FLAGS) {
             // producer row: plane q reuses the slot of plane q - STAGES, which every consumer row releases at the end
@@ -564,6 +578,7 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.px = g.px; P.pm = g.pm; P.mstride = g.mstride; P.mask = a.mask; P.nstride = g.nstride; P.pstride = g.pstride;
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1();
     P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
+    P.l2hint = a.l2hint;
     const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, TY - 2);
     const int nz = P.zout1 - P.zout0;
     // z-chunks: every chunk recomputes one element layer and pays a prologue, and the grid runs in waves

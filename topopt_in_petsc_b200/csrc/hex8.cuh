@@ -41,6 +41,7 @@ struct SpmvArgs {
     const double* a1 = nullptr;          // CHEB: dinv
     double* o1 = nullptr;                // CHEB: d (in/out)
     double s0 = 0, s1 = 0;               // CHEB: d = s0*d + s1*dinv*(b - A u); y = u + d
+    int l2hint = 0;                      // L2 eviction hints for the TMA loads (Jacobi-PCG; tob_ctx_impl::l2hint)
 };
 
 // y = N.(K (N.u)) + (1-N).u on the owned planes of level grid g; *nparts = number of per-CTA partial

@@ -322,6 +322,8 @@ __device__ __forceinline__ double sum_parts_bcast(const double* __restrict__ p, 
     return s;
 }
 
+// H = L2 hint mask (common.cuh): bit 0 streams evict_first, bit 1 p evict_last, bit 2 q last-use / r keep
+template <int H>
 __global__ void __launch_bounds__(kFlatThreads)
 k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
                   const double* __restrict__ dinv, long long n, const double* __restrict__ pq_parts, int n_pq,
@@ -334,6 +336,7 @@ k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* 
         const double rz = sum_parts_bcast(prev_parts + nb_prev, nb_prev, red, &bc);
         alpha = rz / pq;
     }
+    const uint64_t pf = l2_policy_first(), pl = l2_policy_last();
     double rr = 0.0, rz2 = 0.0;
     long long n2 = n >> 1;
     double2* x2 = reinterpret_cast<double2*>(x);
@@ -342,14 +345,17 @@ k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* 
     const double2* q2 = reinterpret_cast<const double2*>(q);
     const double2* d2 = reinterpret_cast<const double2*>(dinv);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-        double2 rv = r2[i];
+        double2 rv = (H & 1) ? ld2_hint(r2 + i, pf) : r2[i];
         if (pq_parts) {
-            double2 xv = x2[i], pv = p2[i], qv = q2[i];
+            double2 xv = (H & 1) ? ld2_hint(x2 + i, pf) : x2[i];
+            const double2 pv = (H & 2) ? ld2_hint(p2 + i, pl) : p2[i];
+            const double2 qv = (H & 4) ? ld2_hint(q2 + i, pf) : q2[i];
             xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
             rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
-            x2[i] = xv; r2[i] = rv;
+            if (H & 1) st2_hint(x2 + i, xv, pf); else x2[i] = xv;
+            if ((H & 1) && !(H & 4)) st2_hint(r2 + i, rv, pf); else r2[i] = rv;  // bit 2: keep the new r for update_p
         }
-        const double2 dv = d2[i];
+        const double2 dv = (H & 1) ? ld2_hint(d2 + i, pf) : d2[i];
         rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
         rz2 = fma(rv.x * dv.x, rv.x, rz2); rz2 = fma(rv.y * dv.y, rv.y, rz2);
     }
@@ -358,6 +364,7 @@ k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* 
     if (threadIdx.x == 0) { out_parts[blockIdx.x] = rr; out_parts[gridDim.x + blockIdx.x] = rz2; }
 }
 
+template <int H>
 __global__ void __launch_bounds__(kFlatThreads)
 k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ dinv, long long n,
                  const double* __restrict__ new_parts, const double* __restrict__ old_parts, int nb) {
@@ -369,23 +376,33 @@ k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const dou
         const double rz_old = sum_parts_bcast(old_parts + nb, nb, red, &bc);
         beta = rz_new / rz_old;
     }
+    const uint64_t pf = l2_policy_first(), pl = l2_policy_last();
     long long n2 = n >> 1;
     double2* p2 = reinterpret_cast<double2*>(p);
     const double2* r2 = reinterpret_cast<const double2*>(r);
     const double2* d2 = reinterpret_cast<const double2*>(dinv);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-        double2 rv = r2[i], dv = d2[i];
-        double2 pv = old_parts ? p2[i] : make_double2(0.0, 0.0);
+        const double2 rv = (H & 5) ? ld2_hint(r2 + i, pf) : r2[i];  // last use of r in this iteration
+        const double2 dv = (H & 1) ? ld2_hint(d2 + i, pf) : d2[i];
+        double2 pv = old_parts ? ((H & 2) ? ld2_hint(p2 + i, pl) : p2[i]) : make_double2(0.0, 0.0);
         pv.x = fma(beta, pv.x, rv.x * dv.x); pv.y = fma(beta, pv.y, rv.y * dv.y);
-        p2[i] = pv;
+        if (H & 2) st2_hint(p2 + i, pv, pl); else p2[i] = pv;
     }
 }
+
+#define TOB_L2HINT_SWITCH(mask, CALL) \
+    switch ((mask) & 7) {             \
+        case 1: { constexpr int HM = 1; CALL; } break; \
+        case 3: { constexpr int HM = 3; CALL; } break; \
+        case 7: { constexpr int HM = 7; CALL; } break; \
+        default: { constexpr int HM = 0; CALL; } break; \
+    }
 
 int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const double* dinv,
                     const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out) {
     const int nb = flat_grid(c, g.own_len);
-    k_pcg_update_xr_f<<<nb, kFlatThreads, 0, c->stream>>>(x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off, dinv + g.own_off,
-                                                        g.own_len, pq_parts, n_pq, prev_parts, nb, out_parts);
+    TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM><<<nb, kFlatThreads, 0, c->stream>>>(
+        x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off, dinv + g.own_off, g.own_len, pq_parts, n_pq, prev_parts, nb, out_parts)));
     c->launches++;
     TOB_KERNEL_CHECK();
     if (nb_out) *nb_out = nb;
@@ -394,7 +411,8 @@ int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, c
 int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const double* dinv, const double* new_parts,
                    const double* old_parts) {
     const int nb = flat_grid(c, g.own_len);
-    k_pcg_update_p_f<<<nb, kFlatThreads, 0, c->stream>>>(p + g.own_off, r + g.own_off, dinv + g.own_off, g.own_len, new_parts, old_parts, nb);
+    TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_p_f<HM><<<nb, kFlatThreads, 0, c->stream>>>(p + g.own_off, r + g.own_off, dinv + g.own_off,
+                                                                                     g.own_len, new_parts, old_parts, nb)));
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;
