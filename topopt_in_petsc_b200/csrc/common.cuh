@@ -117,8 +117,10 @@ struct tob_ctx_impl {
     long long launches = 0;
     // L2 eviction hints in the Jacobi-PCG kernels (env TOB_L2HINT, bit mask): 1 = once-per-iteration streams
     // (x, r, dinv, E) evict_first, 2 = search direction p evict_last, 4 = q / r: stored with normal priority,
-    // evict_first at their last read
-    int l2hint = 0;
+    // evict_first at their last read, 8 = reserve the persisting L2 set-aside for the evict_last lines.
+    // Measured on cfg2 (profiles/r01_l2hint_ab.txt): 0 -> 4.38, 1 -> 4.45, 3 -> 4.60, 7 -> 4.23 design it/s; with the
+    // set-aside (8) 3.2-4.5: the default is 3.
+    int l2hint = 3;
     DevBuf stage[8];  // staging buffers for host<->device vectors
     // TMA encode entry point
     void* encode_tiled = nullptr;

@@ -122,6 +122,14 @@ int tob_ctx_create(const tob_grid_desc* d, tob_ctx** out) {
     if (prop.major < 9) TOB_FAIL("libtopopt_b200 needs TMA/mbarrier hardware (built for sm_100a)");
     c->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("TOB_L2HINT")) c->l2hint = atoi(e);
+    if (c->l2hint & 8) {
+        // evict_last lines are only protected inside the persisting set-aside of the L2 (default size 0)
+        size_t want = (size_t)prop.persistingL2CacheMaxSize;
+        if (const char* e = getenv("TOB_L2_PERSIST_MB")) want = std::min(want, (size_t)atoi(e) << 20);
+        TOB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        if (getenv("TOB_VERBOSE")) fprintf(stderr, "[tob] persisting L2 set-aside %zu MB (max %d MB, L2 %d MB)\n", want >> 20,
+                                           prop.persistingL2CacheMaxSize >> 20, prop.l2CacheSize >> 20);
+    }
     if (d->stream) { c->stream = (cudaStream_t)d->stream; c->own_stream = false; }
     else { TOB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     TOB_CUDA(cudaEventCreate(&c->ev0));
