@@ -342,6 +342,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
         const unsigned char* mptr = P.mask + ((long long)pfirst * P.mstride + (long long)j * P.pm + i);
         const int o = ty * ZM_W + tx + 1;  // my node inside a component tile
         const int o2 = ty * 32 + tx;       // my slot in the exchange buffers
+        long long yoff = (long long)pfirst * P.pstride + (long long)j * P.px + i;  // my node on the plane completed by the current step
 
         // face modes of one plane tile: X stage on rows j and j+1, then Y stage; also hands back my own nodal
         // value (the Dirichlet / dot-product operand of the NEXT step's output, kept in registers)
@@ -493,7 +494,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 
             const int e = pfirst + t;  // node plane completed by this step
             if (outthr && e >= z0) {
-                const long long idx0 = e * P.pstride + (long long)j * P.px + i;
+                const long long idx0 = yoff;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     const long long idx = idx0 + c * P.nstride;
@@ -516,6 +517,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                     }
                 }
             }
+            yoff += P.pstride;
             if (FLAGS) {  // this row is done with plane pidx and with the exchange slot of step t
                 __syncwarp();
                 if (tx == 0) mbar_arrive(&ebars[pidx % L::STAGES]);
