@@ -3,6 +3,7 @@
 // formed -- its weights depend only on the index offset, so H x is a (2s+1)^3 convolution with a
 // clipped box, and Hs = H 1 (Filter.cc:445-448) is the same sum with x = 1.
 #include "filter.cuh"
+#include "tma.cuh"
 #include "vecops.cuh"
 
 namespace tob {
@@ -63,6 +64,118 @@ k_cone(const double* __restrict__ in, double* __restrict__ out, const double* __
     out[nidx] = v;
 }
 
+// ---- TMA-tiled cone filter (modes 0-2, s = 1 or 2) ------------------------------------------------------------
+// One CTA produces a 32 x 8 x CT_Z block of outputs.  A single TMA box load brings the block plus its s-wide rim
+// into shared memory; everything outside the stored field (domain boundary, pitch padding, layers beyond the ghost
+// range) is zero-filled by the TMA unit, which is exactly the clipped box of Filter.cc:417-419 for the weighted sum
+// (the matching weight sum Hs is precomputed once, mode 3 of k_cone).  Each thread owns one (i,j) column: it walks
+// the CT_Z + 2s planes of the box once, loads each of the (2s+1)^2 neighbours of a plane ONCE and scatters it into
+// the up to 2s+1 output layers it belongs to (5x fewer shared-memory reads than a gather per output); the (s+1)^3
+// distinct weights (they depend on |di|,|dj|,|dk| only) live in registers.
+// HBM traffic: the field once (+ rim), Hs once, output once  ~ 24-32 B/element instead of (2s+1)^3 cached reads.
+constexpr int CT_X = 32, CT_Y = 8, CT_Z = 8;
+struct ConeTileParams {
+    const double* hs;    // Hs, filter layout
+    const double* xnat;  // mode 2: x, natural order
+    const double* wtab;  // (2s+1)^3 weights
+    double* out;         // natural order (owned layers)
+    int nex, ney, pe, l0, l1, mode;
+    long long estride;
+};
+template <int S>
+struct ConeTile {
+    static constexpr int SP = (S + 1) & ~1;        // x rim padded to an even count: 16-byte aligned TMA start column
+    static constexpr int BW = CT_X + 2 * SP, BH = CT_Y + 2 * S, BD = CT_Z + 2 * S;
+    static constexpr int BOX_BYTES = BW * BH * BD * 8;
+    static constexpr int SMEM = BOX_BYTES + 128;   // + mbarrier
+};
+
+template <int S>
+__global__ void __launch_bounds__(CT_X * CT_Y)
+k_cone_tiled(const __grid_constant__ CUtensorMap tm, const __grid_constant__ ConeTileParams P) {
+    using T = ConeTile<S>;
+    extern __shared__ __align__(128) unsigned char cone_smem[];
+    const double* box = reinterpret_cast<const double*>(cone_smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(cone_smem + T::BOX_BYTES);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i0 = blockIdx.x * CT_X, j0 = blockIdx.y * CT_Y, l0 = P.l0 + blockIdx.z * CT_Z;
+    if (tx == 0 && ty == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, T::BOX_BYTES);
+        tma_load_3d(cone_smem, &tm, bar, i0 - T::SP, j0 - S, l0 - S);
+    }
+    // distinct weights w[|dk|][|dj|][|di|] while the box is in flight
+    constexpr int W1 = 2 * S + 1;
+    double w[S + 1][S + 1][S + 1];
+#pragma unroll
+    for (int a = 0; a <= S; a++)
+#pragma unroll
+        for (int b = 0; b <= S; b++)
+#pragma unroll
+            for (int c = 0; c <= S; c++) w[a][b][c] = __ldg(P.wtab + ((a + S) * W1 + (b + S)) * W1 + (c + S));
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    mbar_wait(bar, 0);
+
+    double acc[CT_Z];
+#pragma unroll
+    for (int o = 0; o < CT_Z; o++) acc[o] = 0.0;
+    const double* col = box + (ty + S) * T::BW + (tx + T::SP);
+#pragma unroll
+    for (int zp = 0; zp < T::BD; zp++) {  // box plane zp holds local layer l0 - S + zp
+#pragma unroll
+        for (int dj = -S; dj <= S; dj++)
+#pragma unroll
+            for (int di = -S; di <= S; di++) {
+                const double v = col[(zp * T::BH + dj) * T::BW + di];
+#pragma unroll
+                for (int dk = -S; dk <= S; dk++) {
+                    const int o = zp - S - dk;  // output layer (tile-local) that sees this plane at offset dk
+                    if (o >= 0 && o < CT_Z) acc[o] = fma(w[dk < 0 ? -dk : dk][dj < 0 ? -dj : dj][di < 0 ? -di : di], v, acc[o]);
+                }
+            }
+    }
+    const int i = i0 + tx, j = j0 + ty;
+    if (i >= P.nex || j >= P.ney) return;
+#pragma unroll
+    for (int o = 0; o < CT_Z; o++) {
+        const int l = l0 + o;
+        if (l >= P.l1) break;
+        const long long nidx = (long long)i + (long long)P.nex * (j + (long long)P.ney * (l - P.l0));
+        double v = acc[o];
+        if (P.mode != 1) v /= P.hs[l * P.estride + (long long)j * P.pe + i];
+        if (P.mode == 2) v /= P.xnat[nidx];
+        P.out[nidx] = v;
+    }
+}
+
+template <int S>
+static int cone_apply_tiled(tob_filter_impl* h, const double* in_st, double* out, const double* xnat, int mode) {
+    using T = ConeTile<S>;
+    tob_ctx_impl* c = h->c;
+    const LevelGrid& g = c->g0;
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)g.nex, (cuuint64_t)g.ney, (cuuint64_t)h->nl};
+    cuuint64_t str[2] = {(cuuint64_t)g.pe * 8, (cuuint64_t)h->estride * 8};
+    cuuint32_t bx[3] = {(cuuint32_t)T::BW, (cuuint32_t)T::BH, (cuuint32_t)T::BD};
+    TOB_CHECK(encode_map(c, &tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, in_st, dims, str, bx));
+    ConeTileParams P;
+    P.hs = h->hs_st; P.xnat = xnat; P.wtab = h->wtab; P.out = out;
+    P.nex = g.nex; P.ney = g.ney; P.pe = g.pe; P.l0 = h->own0; P.l1 = h->own1; P.mode = mode; P.estride = h->estride;
+    auto kern = k_cone_tiled<S>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+        attr_set = true;
+    }
+    dim3 grid(div_up(g.nex, CT_X), div_up(g.ney, CT_Y), div_up(h->own1 - h->own0, CT_Z));
+    kern<<<grid, dim3(CT_X, CT_Y), T::SMEM, c->stream>>>(tm, P);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
 static int fhalo(tob_filter_impl* h, double* v) {
     tob_ctx_impl* c = h->c;
     if (c->desc.nranks == 1) return 0;
@@ -78,6 +191,10 @@ static int cone_apply(tob_filter_impl* h, const double* in_st, double* out, cons
     tob_ctx_impl* c = h->c;
     const LevelGrid& g = c->g0;
     int l0 = h->own0, l1 = h->own1;
+    if (mode != 3 && h->tiled) {
+        if (h->s == 1) return cone_apply_tiled<1>(h, in_st, out, xnat, mode);
+        if (h->s == 2) return cone_apply_tiled<2>(h, in_st, out, xnat, mode);
+    }
     if (mode == 3) { l0 = 0; l1 = h->nl; }
     dim3 grid(div_up(g.nex, 128), g.ney, l1 - l0);
     k_cone<<<grid, 128, 0, c->stream>>>(in_st, out, h->wtab, xnat, g.nex, g.ney, g.nez, g.pe, h->estride, h->s, h->gl0, l0,
@@ -155,6 +272,7 @@ int filter_create(tob_ctx_impl* c, int type, double rmin, tob_filter_impl** out)
         s = std::min(s, std::min((g.nxn - 1) / 2, std::min((g.nyn - 1) / 2, (g.nzn - 1) / 2)));
         if (s < 0) s = 0;
         h->s = s;
+        h->tiled = !(getenv("TOB_CONE_TILED") && atoi(getenv("TOB_CONE_TILED")) == 0);  // 0: direct-gather kernel (A/B, cross-check)
         const int lo = std::min(s, g.ke0), hi = std::min(s, g.nez - g.ke1);
         h->gl0 = g.ke0 - lo;
         h->own0 = lo;

@@ -12,6 +12,7 @@ struct tob_filter_impl {
     double R = 0.0;
     // cone filter: element field with s ghost layers on each side (clipped by the domain)
     int s = 0;              // ElemConn
+    bool tiled = true;      // TMA-tiled kernel for s = 1, 2 (else the direct-gather kernel)
     int gl0 = 0;            // global index of local layer 0
     int own0 = 0, own1 = 0; // owned local layers
     int nl = 0;             // stored local layers
