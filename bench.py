@@ -12,8 +12,10 @@ filtering, MMA update, density filter, MND) on the synthetic cantilever of BASEL
 `e2e`   : the same loop driven through the C-ABI with HOST (pinned) buffers -- every call stages its
           vectors host<->device inside the timed region, exactly what the reference's main.cc/MMA.cc
           do through VecGetArray.
-`roofline`: the fine-level matrix-free SpMV kernel, timed live with CUDA event pairs around every launch
-          inside the timed region; algorithmic bytes = 8*nel + 16*ndof per application.
+`roofline`: the fine-level matrix-free SpMV kernel, timed live with CUDA event pairs around every 8th launch of the
+          eager part of the timed region (pairs around every launch cost 6 % of a PCG iteration); algorithmic
+          bytes = 8*nel + 16*ndof per application.
+`gmg_solver`: the same design iterations with the multigrid-preconditioned solver (secondary leg, N >= 1).
 `cpu_baseline`: the C/OpenMP restatement of the reference's assembled-CSR path (oracle/c/cpu_ref.c) timed
           on the host cores on a bounded sample (see `sample`).
 """

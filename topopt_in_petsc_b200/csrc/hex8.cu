@@ -569,8 +569,8 @@ static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& 
 
 int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     if (nparts) *nparts = 0;
-    // measured (profiles/r01_spmv_probe_v4.txt): the mbarrier hand-off kernel with 32x16 tiles wins at every size tried
-    // (192x96x96: 49 us vs 54 (ZM16R) / 65 (ZM8R); 256^3: 0.368 ms vs 0.422 / 0.428)
+    // measured (profiles/r01_spmv_probe_v6.txt): the mbarrier hand-off kernel with 32x16 tiles wins at every size tried
+    // (192x96x96: 43 us vs 49 (same tile, __syncthreads) / 57-61 (32x8 tiles); 256^3: 0.325 ms vs 0.385 / 0.362-0.391)
     int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM16RF : a.kernel;
     if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
     if (kernel == SPMV_NAIVE) {
