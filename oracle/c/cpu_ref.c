@@ -12,8 +12,9 @@
  *     is Jacobi-preconditioned CG on the same assembled matrix, i.e. the same algorithm as the GPU
  *     arm's cfg2 solver, so both arms do identical numerical work per iteration.
  *   - objective / sensitivities, LinearElasticity.cc:403-437.
- * PARITY STATUS: parity unpinned (the reference has no tests); cross-checked against the
- * independent numpy oracle in tests/test_oracle_cpu.py.
+ * PARITY STATUS: pinned through the numpy oracle (tests/test_oracle_cpu.py), which reproduces the output of the
+ * reference's own unmodified program run on oracle/petsc_lite (tests/test_reference_cpu.py,
+ * tests/golden/reference_runs.json).
  */
 #include <math.h>
 #include <omp.h>

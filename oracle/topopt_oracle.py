@@ -5,13 +5,17 @@ state solve, objective/sensitivities and the design filters.  It is imported
 only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg -- the
 product path (topopt_in_petsc_b200/ + libtopopt_b200.so) never touches it.
 
-PARITY STATUS: the reference ships no tests, fixtures or golden outputs and
-needs PETSc+MPI (absent here), so this oracle is *parity unpinned* for the
-physics/filter part; it is pinned instead by (i) the surveyor's independent
-known answers (tests/golden/appendix_c.json), (ii) an
-independent C restatement (oracle/c/) that must agree with it, and (iii) for
-the MMA optimiser, by the reference's own unmodified MMA.cc compiled against a
-stub petsc.h into oracle/_ref/ (see oracle/Makefile).
+PARITY STATUS: pinned by the reference's own code.  The reference ships no tests or
+fixtures and its build needs PETSc + MPI (absent here), but its seven source files
+compile unmodified, where they lie, against oracle/petsc_lite -- a serial restatement
+of the PETSc/MPI slice they call (KSPSolve replaced by an exact Jacobi-PCG solve) --
+into oracle/_ref/topopt_ref (oracle/Makefile).  tests/test_reference_cpu.py checks this
+oracle's design loop against that program's output (tests/golden/reference_runs.json:
+printed history to the printed 6 decimals, final design field to 1e-10) for the
+density, sensitivity and PDE filters and the Heaviside projection.  Also pinned by
+(i) the surveyor's known answers (tests/golden/appendix_c.json),
+(ii) the independent C restatement (oracle/c/), (iii) the reference's unmodified MMA.cc
+as a library (oracle/_ref/libmma_ref.so, tests/test_mma_ref.py).
 
 Every function cites the reference file:line (paths relative to the reference
 checkout) it restates.  Numbering conventions:

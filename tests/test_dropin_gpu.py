@@ -1,7 +1,7 @@
 """Drop-in boundary on the GPU: the reference's UNTOUCHED main.cc + MMA.cc linked against the B200 classes
 (oracle/_ref/topopt_dropin, built by oracle/Makefile in the container that has /root/reference) and the
 product's own driver (host/topopt_b200, device MMA) must print the same optimisation history, and that
-history must match the CPU oracle's restatement of main.cc."""
+history must match the CPU oracle's restatement of main.cc and the golden history of the reference's own program."""
 import os
 import re
 import subprocess
@@ -56,6 +56,21 @@ def test_own_driver_matches_oracle(oracle, tmp_path):
     assert conn.max() == npts - 1 and int(offs[-1]) == 8 * ncells and set(typ.tolist()) == {12}
     assert abs(float(pts[:, 0].max()) - 2.0) < 1e-6 and abs(float(pts[:, 2].max()) - 1.0) < 1e-6
     assert 0.0 <= float(dumps[-1][2][2].min()) and float(dumps[-1][2][2].max()) <= 1.0  # xPhys in [0,1]
+
+
+def test_own_driver_matches_reference_golden(tmp_path):
+    """Against the reference's own code: tests/golden/reference_runs.json holds the history the reference's unmodified
+    program prints for this very command line when run serially on oracle/petsc_lite (make_reference_golden.py)."""
+    import json
+    fix = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_runs.json")))
+    case = [c for c in fix["cases"] if c["name"] == "density_17x9x9"][0]
+    assert case["shape"] == [17, 9, 9] and case["iters"] == 4 and case["args"] == ["-rmin", "0.3"]
+    h = history(run([DRIVER] + ARGS, tmp_path))
+    ref = np.array(case["history"])
+    assert h.shape == ref.shape == (4, 6)
+    assert np.array_equal(h[:, 0], ref[:, 0])
+    assert np.abs(h[:, 1] - ref[:, 1]).max() <= 2e-6 * ref[:, 1].max()   # true compliance, both printed with %f
+    assert np.abs(h[:, 2:] - ref[:, 2:]).max() <= 3e-6                    # scaled fx (<= 10), gx, ch, mnd
 
 
 def test_untouched_main_and_mma_dropin(tmp_path):

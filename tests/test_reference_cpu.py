@@ -1,0 +1,73 @@
+"""CPU: the oracles against the REFERENCE'S OWN CODE.
+
+tests/golden/reference_runs.json holds outputs of oracle/_ref/topopt_ref -- the reference's unmodified main.cc,
+TopOpt.cc, LinearElasticity.cc, Filter.cc, PDEFilter.cc, MMA.cc and MPIIO.cc running serially against
+oracle/petsc_lite (generator: tests/golden/make_reference_golden.py).  Here
+  * the numpy oracle's restatement of the design loop must reproduce them: the printed history to the 6 decimals
+    main.cc prints, the final design field to 1e-10 -- for the density, sensitivity and PDE filters and the projection;
+  * where the binary exists (the container that has /root/reference; it also travels to the GPU box) it is re-run and
+    must reproduce the fixture exactly, and its result container must read back with the layout the product writes.
+Tolerances: history 1e-6 absolute (print rounding of %f), design fields 1e-10, sums 1e-9."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import make_reference_golden as G  # noqa: E402
+
+FIX = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_runs.json")))
+CASES = {c["name"]: c for c in FIX["cases"]}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_numpy_oracle_reproduces_reference_run(oracle, name):
+    c = CASES[name]
+    g = oracle.Grid(*c["shape"])
+    res = oracle.run_design_loop(g, c["iters"], solve_tol=1e-12, **c["oracle"])
+    got = np.array([[r["itr"], r["fx"], r["fscaled"], r["gx"], r["ch"], r["mnd"]] for r in res["hist"]])
+    ref = np.array(c["history"])
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-6, np.abs(got - ref).max()
+    st = c["stride"]
+    assert np.abs(res["x"][::st] - np.array(c["x"])).max() <= 1e-10
+    assert np.abs(res["xPhys"][::st] - np.array(c["xPhys"])).max() <= 1e-10
+    assert abs(res["x"].sum() - c["x_sum"]) <= 1e-9 and abs(res["xPhys"].sum() - c["xPhys_sum"]) <= 1e-9
+    assert abs(np.linalg.norm(res["U"]) - c["U_norm"]) <= 1e-8 * c["U_norm"] and res["U"].size == c["U_size"]
+    # fscale survives the reference's "%e" restart file only to 7 digits (TopOpt.cc:553)
+    assert abs(res["fscale"] - c["restart_fscale"]) <= 1e-6 * c["restart_fscale"] and c["restart_itr"] == c["iters"]
+
+
+def test_golden_problem_sizes_bit_exact(oracle):
+    for c in FIX["cases"]:
+        g = oracle.Grid(*c["shape"])
+        n = -(-g.nel // c["stride"])
+        assert len(c["x"]) == n and len(c["xPhys"]) == n and c["U_size"] == g.ndof  # nel, ndof: TopOpt.cc:172-175
+
+
+@pytest.mark.skipif(not os.path.exists(G.REF), reason="oracle/_ref/topopt_ref not built (needs /root/reference at build time)")
+def test_reference_binary_reproduces_fixture_and_container_layout(tmp_path):
+    c = CASES["density_17x9x9"]
+    stdout, d = G.run_reference(c, str(tmp_path))
+    assert G.parse_history(stdout) == c["history"]
+    vecs = G.read_petsc_vecs(os.path.join(d, "Restart00.dat"))
+    assert len(vecs) == 6  # x, xPhys, xo1, xo2, U(asymptote), L(asymptote): TopOpt.cc:556-562
+    assert np.array_equal(vecs[0][::c["stride"]], np.array(c["x"]))
+    # result container written by the reference's MPIIO.cc through petsc_lite's MPI_File: the reader the GPU tests use
+    # for the product's container (tests/test_dropin_gpu.py::parse_container) must read it too
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import importlib
+    td = importlib.import_module("test_dropin_gpu")
+    pts, conn, offs, typ, dumps = td.parse_container(os.path.join(d, "output_00000.dat"))
+    nx, ny, nz = c["shape"]
+    assert len(pts) == nx * ny * nz and len(conn) == (nx - 1) * (ny - 1) * (nz - 1)
+    assert os.path.getsize(os.path.join(d, "output_00000.dat")) == c["container_bytes"]
+    assert [dmp[0] for dmp in dumps] == [1, 2, 3, 4, 5]  # main.cc:115,129: every iteration + the final dump as itr+1
+    assert conn[0].tolist() == [0, 1, nx + 1, nx, nx * ny, nx * ny + 1, nx * ny + nx + 1, nx * ny + nx]
+    assert int(offs[-1]) == 8 * len(conn) and set(typ.tolist()) == {12}
+    assert abs(float(pts[:, 0].max()) - 2.0) < 1e-6 and abs(float(pts[:, 1].max()) - 1.0) < 1e-6
+    xphys_last = dumps[-1][2][2]
+    assert np.abs(xphys_last - vecs[1].astype(np.float32)).max() <= 1e-6  # cell field 3 = xPhys, fp32
