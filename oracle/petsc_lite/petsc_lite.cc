@@ -19,7 +19,31 @@ struct _p_Vec {
 };
 struct _p_Mat {
     PetscInt m, n;
-    std::vector<std::map<PetscInt, PetscScalar>> rows;
+    std::vector<std::map<PetscInt, PetscScalar>> rows;  // assembly form
+    // CSR snapshot for the products (rebuilt lazily after any modification)
+    bool csr_valid = false;
+    std::vector<PetscInt> rp, ci;
+    std::vector<PetscScalar> va;
+    void csr() {
+        if (csr_valid) return;
+        rp.assign((size_t)m + 1, 0);
+        size_t nnz = 0;
+        for (PetscInt i = 0; i < m; i++) { nnz += rows[(size_t)i].size(); rp[(size_t)i + 1] = (PetscInt)nnz; }
+        ci.resize(nnz);
+        va.resize(nnz);
+        size_t k = 0;
+        for (PetscInt i = 0; i < m; i++)
+            for (const auto& kv : rows[(size_t)i]) { ci[k] = kv.first; va[k] = kv.second; k++; }
+        csr_valid = true;
+    }
+    void apply(const PetscScalar* x, PetscScalar* y) {
+        csr();
+        for (PetscInt i = 0; i < m; i++) {
+            PetscScalar s = 0;
+            for (PetscInt k = rp[(size_t)i]; k < rp[(size_t)i + 1]; k++) s += va[(size_t)k] * x[ci[(size_t)k]];
+            y[i] = s;
+        }
+    }
 };
 struct _p_PC {
     std::string type = "none";
@@ -297,6 +321,7 @@ PetscErrorCode MatSetValuesLocal(Mat A, PetscInt m, const PetscInt* rows, PetscI
     for (PetscInt i = 0; i < m; i++) {
         if (rows[i] < 0) continue;  // PETSc ignores negative indices
         if (rows[i] >= A->m) return 63;
+        A->csr_valid = false;
         auto& row = A->rows[(size_t)rows[i]];
         for (PetscInt j = 0; j < n; j++) {
             if (cols[j] < 0) continue;
@@ -310,6 +335,7 @@ PetscErrorCode MatSetValuesLocal(Mat A, PetscInt m, const PetscInt* rows, PetscI
 PetscErrorCode MatAssemblyBegin(Mat, MatAssemblyType) { return 0; }
 PetscErrorCode MatAssemblyEnd(Mat, MatAssemblyType) { return 0; }
 PetscErrorCode MatZeroEntries(Mat A) {
+    A->csr_valid = false;
     for (auto& r : A->rows)
         for (auto& kv : r) kv.second = 0.0;
     return 0;
@@ -317,11 +343,7 @@ PetscErrorCode MatZeroEntries(Mat A) {
 PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
     if (x->n != A->n || y->n != A->m) return 60;
     std::vector<PetscScalar> out((size_t)A->m);
-    for (PetscInt i = 0; i < A->m; i++) {
-        PetscScalar s = 0;
-        for (const auto& kv : A->rows[(size_t)i]) s += kv.second * x->a[kv.first];
-        out[(size_t)i] = s;
-    }
+    A->apply(x->a, out.data());
     memcpy(y->a, out.data(), sizeof(PetscScalar) * (size_t)A->m);
     return 0;
 }
@@ -334,11 +356,13 @@ PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y) {
     return 0;
 }
 PetscErrorCode MatDiagonalScale(Mat A, Vec l, Vec r) {  // A <- diag(l) A diag(r)
+    A->csr_valid = false;
     for (PetscInt i = 0; i < A->m; i++)
         for (auto& kv : A->rows[(size_t)i]) kv.second *= (l ? l->a[i] : 1.0) * (r ? r->a[kv.first] : 1.0);
     return 0;
 }
 PetscErrorCode MatDiagonalSet(Mat A, Vec d, InsertMode mode) {
+    A->csr_valid = false;
     for (PetscInt i = 0; i < A->m && i < A->n; i++) {
         if (mode == ADD_VALUES) A->rows[(size_t)i][i] += d->a[i];
         else A->rows[(size_t)i][i] = d->a[i];
@@ -538,13 +562,7 @@ PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
         const PetscScalar d = it == A->rows[(size_t)i].end() ? 0.0 : it->second;
         dinv[(size_t)i] = d != 0.0 ? 1.0 / d : 1.0;
     }
-    auto apply = [&](const PetscScalar* u, PetscScalar* y) {
-        for (PetscInt i = 0; i < n; i++) {
-            PetscScalar s = 0;
-            for (const auto& kv : A->rows[(size_t)i]) s += kv.second * u[kv.first];
-            y[i] = s;
-        }
-    };
+    auto apply = [&](const PetscScalar* u, PetscScalar* y) { A->apply(u, y); };
     PetscReal bnorm = 0;
     for (PetscInt i = 0; i < n; i++) bnorm += b->a[i] * b->a[i];
     bnorm = sqrt(bnorm);

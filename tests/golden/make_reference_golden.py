@@ -10,7 +10,11 @@ on a few small cantilevers covering the three filter types and the Heaviside pro
 The fixtures travel to the GPU box (where /root/reference does not exist); tests/test_reference_cpu.py checks the numpy
 oracle and -- where the binary exists -- the binary itself against them.
 
-Usage (in the container that has /root/reference):  make -C oracle && python tests/golden/make_reference_golden.py
+With --big it also runs the two grids of the surveyor's known answers (48x24x24 and the reference default
+64x32x32, uniform density 0.12) for ONE design iteration and stores the compliance the reference prints (minutes of CPU
+time and gigabytes of std::map matrix: petsc_lite is built for fidelity, not speed); without it the stored values are kept.
+
+Usage (in the container that has /root/reference):  make -C oracle && python tests/golden/make_reference_golden.py [--big]
 """
 import json
 import os
@@ -57,7 +61,7 @@ def run_reference(case, workdir=None):
     d = workdir or tempfile.mkdtemp()
     nx, ny, nz = case["shape"]
     cmd = [REF, "-nx", str(nx), "-ny", str(ny), "-nz", str(nz), "-nlvls", "1", "-maxItr", str(case["iters"]), "-restart", "1"] + case["args"]
-    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=3600)
     assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
     return r.stdout, d
 
@@ -79,13 +83,24 @@ def main():
         usol = read_petsc_vecs(os.path.join(d, "RestartSol00.dat"))[0]
         itr, fscale = open(os.path.join(d, "Restart00_itr_f0.dat")).read().split()
         x, xphys = vecs[0], vecs[1]
+        m = re.search(r"results in a stencil of (\d+) elements", stdout)  # Filter.cc:334 (cone filters only)
         st = sample_stride(x.size)
         out["cases"].append(dict(name=case["name"], shape=case["shape"], iters=case["iters"], args=case["args"], oracle=case["oracle"],
                                  history=hist, stride=st, x=[float(v) for v in x[::st]], xPhys=[float(v) for v in xphys[::st]],
                                  x_sum=float(x.sum()), xPhys_sum=float(xphys.sum()), U_norm=float(np.linalg.norm(usol)),
-                                 U_size=int(usol.size), restart_itr=int(itr), restart_fscale=float(fscale),
+                                 U_size=int(usol.size), restart_itr=int(itr), restart_fscale=float(fscale), elemconn=int(m.group(1)) if m else None,
                                  container_bytes=os.path.getsize(os.path.join(d, "output_00000.dat"))))
         print(case["name"], "fx:", [h[1] for h in hist])
+    known = {}
+    if os.path.exists(OUT):
+        known = json.load(open(OUT)).get("known_answers", {})
+    if "--big" in sys.argv:
+        for shape in ([49, 25, 25], [65, 33, 33]):
+            stdout, _ = run_reference(dict(shape=shape, iters=1, args=[]))
+            h = parse_history(stdout)
+            known["x".join(str(v - 1) for v in shape)] = dict(iteration1_true_fx_printed=h[0][1], line=[l for l in stdout.splitlines() if l.startswith("It.: 1")][0])
+            print(shape, h[0])
+    out["known_answers"] = known
     with open(OUT, "w") as f:
         json.dump(out, f, indent=0, separators=(",", ":"))
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
