@@ -332,7 +332,9 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOAD, "elements": [c["nex"], c["ney"], c["nez"]],
                       "note": "PETSc/MPI are not installable here; this arm is the C/OpenMP restatement of the reference's "
-                              "assembled-CSR path (oracle/c/cpu_ref.c) on the host cores"},
+                              "assembled-CSR path (oracle/c/cpu_ref.c) on the host cores.  The reference's own sources do run "
+                              "against oracle/petsc_lite (oracle/_ref/topopt_ref), but serially with std::map matrices: a "
+                              "fidelity tool that pins the oracles, not a timing baseline"},
            "cpu_baseline": cb, "gpu_launches": 0, "wall_seconds": None,
            "e2e": {"value": cb["value"], "unit": "design iterations/s (whole job)", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     out["wall_seconds"] = time.time() - t0
