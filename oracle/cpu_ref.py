@@ -28,6 +28,18 @@ def lib():
         l.cref_pcg.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         l.cref_objective.restype = C.c_double
         l.cref_objective.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_double] * 4 + [C.POINTER(C.c_double)] * 2 + [C.c_void_p]
+        l.cref_mg_setup.restype = C.c_double
+        l.cref_mg_setup.argtypes = [C.c_void_p, C.c_int]
+        l.cref_fgmres_mg.restype = C.c_int
+        l.cref_fgmres_mg.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        l.cref_mg_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        for f in ("cref_level_nnz", "cref_level_ndof"):
+            getattr(l, f).restype = C.c_longlong
+            getattr(l, f).argtypes = [C.c_void_p, C.c_int]
+        l.cref_level_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.cref_mg_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.cref_cone_filter.restype = C.c_double
+        l.cref_cone_filter.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -72,6 +84,40 @@ class CpuRef:
         sec = self.l.cref_objective(self.h, U.ctypes.data, x.ctypes.data, Emin, Emax, penal, volfrac, C.byref(fx),
                                     C.byref(gx), df.ctypes.data)
         return fx.value, gx.value, df, sec
+
+    # ---- the reference's solver configuration: FGMRES + PCMG(Galerkin) + GMRES/SOR smoothers -------------
+    def mg_setup(self, nlvls=4):
+        """KSPSetUp after an operator change (LinearElasticity.cc:198-200): Galerkin products of every level."""
+        sec = self.l.cref_mg_setup(self.h, nlvls)
+        if sec < 0:
+            raise ValueError("mesh dimension not compatible with the number of multigrid levels")
+        return sec
+
+    def fgmres_mg(self, U=None, rtol=1e-5, maxits=200, restart=100):
+        U = np.zeros(self.ndof) if U is None else np.ascontiguousarray(U, dtype=np.float64)
+        rr, sec = C.c_double(), C.c_double()
+        its = self.l.cref_fgmres_mg(self.h, U.ctypes.data, rtol, maxits, restart, C.byref(rr), C.byref(sec))
+        return U, its, rr.value, sec.value
+
+    def mg_apply(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.ndof)
+        self.l.cref_mg_apply(self.h, b.ctypes.data, x.ctypes.data)
+        return x
+
+    def level_matrix(self, l):
+        import scipy.sparse as sp
+        n, nnz = self.l.cref_level_ndof(self.h, l), self.l.cref_level_nnz(self.h, l)
+        rp, col, val = np.empty(n + 1, np.int64), np.empty(nnz, np.int32), np.empty(nnz)
+        self.l.cref_level_csr(self.h, l, rp.ctypes.data, col.ctypes.data, val.ctypes.data)
+        return sp.csr_matrix((val, col, rp), shape=(n, n))
+
+    def cone_filter(self, rmin, x, mode=0):
+        """mode 0: (H x)/Hs (Filter.cc:66-71); mode 1: H (x/Hs) (Filter.cc:178-192)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty(self.nel)
+        sec = self.l.cref_cone_filter(self.h, rmin, mode, x.ctypes.data, out.ctypes.data)
+        return out, sec
 
     def close(self):
         if self.h:

@@ -22,7 +22,7 @@ if a.micro:
     out["copy_gbs_1GiB"] = ctx.microbench_copy(1 << 30)
     ctx.close()
     print(json.dumps(out), flush=True)
-names = {1: "naive_dense", 2: "zmarch_ty8", 3: "zmarch_ty16", 4: "zmarch_ty12_regs", 5: "zmarch_ty8_regs", 6: "zmarch_ty8_mbar", 7: "zmarch_ty16_mbar", 8: "zmarch_ty12_mbar", 9: "zmarch_ty16_regs"}
+names = {1: "naive_dense", 2: "zmarch_ty8", 3: "zmarch_ty16", 4: "zmarch_ty12_regs", 5: "zmarch_ty8_regs", 6: "zmarch_ty8_mbar", 7: "zmarch_ty16_mbar", 8: "zmarch_ty12_mbar", 9: "zmarch_ty16_regs", 10: "zm4_ty16_unroll4", 11: "zm4_ty16_merged_producer"}
 for sz in a.sizes.split(","):
     ex, ey, ez = [int(v) for v in sz.split("x")]
     ctx = Context(ex + 1, ey + 1, ez + 1)

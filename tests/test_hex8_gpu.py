@@ -51,7 +51,7 @@ def test_spmv_parity(oracle, shape, xc, dens):
     ctx = Context(*shape, xc=xc)
     assert ctx.nel == g.nel and ctx.ndof == g.ndof  # bit-exact counts (TopOpt.cc:172-175)
     scale = np.abs(yref).max()
-    for kernel in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+    for kernel in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
         phys = LinearElasticity(ctx, nu=0.3, opts=solver_opts(spmv_kernel=kernel))
         phys.SetDensity(x, 1e-9, 1.0, 3.0)
         y = phys.SpMV(u)

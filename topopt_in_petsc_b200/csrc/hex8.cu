@@ -187,10 +187,10 @@ struct ZmParams {
 // coordinate must be 16-byte aligned (measured: odd fp64 origins raise "illegal instruction"), so the
 // box starts at the even column bx*30-2 and thread tx reads column tx+1.
 constexpr int ZM_W = 34;
-template <int TY, bool FLAGS>
+template <int TY, bool FLAGS, int ROWS = TY>
 struct ZmSmem {
     static constexpr int NT = 32 * TY;
-    static constexpr int NC = ZM_W * TY;          // doubles per component tile
+    static constexpr int NC = ZM_W * ROWS;        // doubles per component tile (ROWS node rows in the TMA box)
     static constexpr int U_BYTES = (3 * NC * 8 + 127) / 128 * 128;  // TMA destinations must be 128-byte aligned
     static constexpr int E_BYTES = (NC * 8 + 127) / 128 * 128;
     static constexpr int TX_BYTES = 4 * NC * 8;                     // bytes the two TMA loads deliver per stage
@@ -492,22 +492,289 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------------------
+// z-march, generation 2: the mbarrier hand-off kernel above with the march unrolled by STAGES (= 4).
+// What the unrolling buys (SASS of the gen-1 loop: 366 instructions per warp-step for 177 DP -- issue slots, not the
+// FP64 pipe, were the binding resource, profiles/r01_ncu_zmarch_ty16_mbar_v3_256.txt):
+//   * the carried state (lower-face modes, own nodal value, mask) ping-pongs between two register sets by NAME, so the
+//     ~33 IMAD.MOV per step of the gen-1 loop disappear;
+//   * ring-slot index, exchange-slot index and the barrier addresses are compile-time constants of the sub-step: the
+//     uniform-datapath index arithmetic (USHF/ULOP3/ULEA/UIADD3, ~28 per step) disappears, shared-memory operands
+//     become base + immediate.
+// Everything else (tile geometry, producer warp, row hand-off protocol) is the gen-1 design.
+// ---------------------------------------------------------------------------------------
+template <int K>
+struct IntC { static constexpr int v = K; };
+
+// MERGED = false: TY node rows per tile, warp row TY-1 is the dedicated TMA producer (15 compute warps of 16: one
+//   scheduler runs 3 compute warps + the producer, the other three 4 compute warps -- those three bound the step).
+// MERGED = true : TY + 1 node rows per tile, every warp owns an element row (4 compute warps on every scheduler, 15
+//   instead of 14 output rows per step); the last row -- the tail of the hand-off wavefront, so the other rows have
+//   released the slot by the time it gets there -- also refills the TMA ring.
+template <int TY, int EPI, bool MERGED>
+__global__ void __launch_bounds__(32 * TY, 1)
+k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmE,
+           const __grid_constant__ Hex8BlocksPacked KB, const __grid_constant__ ZmParams P) {
+    constexpr int ROWS = MERGED ? TY + 1 : TY;   // node rows in the box
+    constexpr int NCOMP = ROWS - 1;              // element rows = compute warps
+    using L = ZmSmem<TY, true, ROWS>;
+    static_assert(L::STAGES == 4 && L::XCH_DEPTH == 4, "the unrolled march assumes 4 ring slots");
+    constexpr int NT = L::NT;
+    constexpr int NC = L::NC;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double red[32];
+    double* xch = reinterpret_cast<double*>(smem_raw + L::STAGES * L::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::BAR_OFF);  // full[4]
+    uint64_t* ebars = bars + L::STAGES;                                   // empty[4]
+    uint64_t* xbars = bars + 2 * L::STAGES;                               // xfull[TY][4]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 31;
+    const int ty = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int i0 = blockIdx.x * 30 - 1, j0 = blockIdx.y * (ROWS - 2) - 1;
+    const int i = i0 + tx, j = j0 + ty;
+    const int z0 = P.zout0 + blockIdx.z * P.zchunk;
+    const int z1 = min(z0 + P.zchunk, P.zout1);
+    const bool outthr = (tx >= 1) && (tx <= 30) && (ty >= 1) && (ty <= ROWS - 2) && (i < P.nxn) && (j < P.nyn);
+    const int pfirst = z0 - 1;
+    const int nplanes = z1 - z0 + 2;
+    double part = 0.0;
+
+    if (z0 < z1) {
+        if (tid == 0) {
+            for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
+            for (int s = 0; s < L::STAGES; s++) mbar_init(&ebars[s], NCOMP);
+            for (int s = 0; s < TY * L::XCH_DEPTH; s++) mbar_init(&xbars[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+
+        auto issue = [&](const int q) {  // plane counter q -> ring slot q & 3
+            const int s = q & 3;
+            unsigned char* st = smem_raw + s * L::STAGE_BYTES;
+            const int p = pfirst + q;
+            mbar_expect_tx(&bars[s], L::TX_BYTES);
+            if (P.l2hint & 2) tma_load_4d_hint(st, &tmU, &bars[s], i0 - 1, j0, 0, p, l2_policy_last());
+            else tma_load_4d(st, &tmU, &bars[s], i0 - 1, j0, 0, p);
+            if (P.l2hint & 1) tma_load_3d_hint(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1, l2_policy_first());
+            else tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
+        };
+        const bool refills = MERGED && ty == TY - 1;
+        if (!MERGED && ty == TY - 1) {
+            // ---- dedicated producer row ----------------------------------------------------------
+            for (int q = 0; q < nplanes; q++) {
+                if (q >= L::STAGES) mbar_wait(&ebars[q & 3], ((q >> 2) - 1) & 1);
+                if (tx == 0) issue(q);
+            }
+        } else {
+            if (refills && tx == 0)
+                for (int q = 0; q < L::STAGES && q < nplanes; q++) issue(q);
+            // ---- consumer rows ---------------------------------------------------------------
+            const bool innode = (i >= 0) && (i < P.nxn) && (j >= 0) && (j < P.nyn);
+            const unsigned char* mptr = P.mask + ((long long)pfirst * P.mstride + (long long)j * P.pm + i);
+            const int o = ty * ZM_W + tx + 1;
+            const int o2 = ty * 32 + tx;
+            double* ybase = P.y + ((long long)pfirst * P.pstride + (long long)j * P.px + i);  // EPI operands share the offset
+            const long long adiff = (EPI == EPI_RESID || EPI == EPI_CHEB) ? (P.a0 - P.y) : 0;
+            const double* su0 = reinterpret_cast<const double*>(smem_raw) + o;  // my node in slot 0, component 0
+            double* xw0 = xch + o2;
+            uint64_t* xb_mine = &xbars[ty * 4];
+            uint64_t* xb_below = &xbars[(ty - 1) * 4];
+            const bool has_below = ty >= 1, signals = ty < NCOMP - 1;
+
+            auto face_modes = [&](const double* su, double (&fm)[12], double (&own)[3]) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double a = su[c * NC], b = su[c * NC + 1], cc = su[c * NC + ZM_W], d = su[c * NC + ZM_W + 1];
+                    const double s0 = a + b, d0 = a - b, s1 = cc + d, d1 = cc - d;
+                    fm[4 * c + 0] = s0 + s1;
+                    fm[4 * c + 1] = d0 + d1;
+                    fm[4 * c + 2] = s0 - s1;
+                    fm[4 * c + 3] = d0 - d1;
+                    own[c] = a;
+                }
+            };
+
+            double fA[12], fB[12], upr[12], uA[3], uB[3];
+            unsigned mA = 0, mB = 0;
+#pragma unroll
+            for (int k = 0; k < 12; k++) { fA[k] = 0.0; fB[k] = 0.0; upr[k] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < 3; c++) { uA[c] = 0.0; uB[c] = 0.0; }
+
+            // prologue: plane pfirst (ring slot 0, phase 0)
+            mbar_wait(&bars[0], 0);
+            mA = (innode && pfirst >= 0) ? (unsigned)*mptr : 0u;
+            mptr += P.mstride;
+            face_modes(su0, fA, uA);
+            __syncwarp();
+            if (tx == 0) mbar_arrive(&ebars[0]);
+            if (refills && L::STAGES < nplanes) {  // plane 4 reuses the slot of plane 0
+                mbar_wait(&ebars[0], 0);
+                if (tx == 0) issue(L::STAGES);
+            }
+
+            // sub-step K of a group of four: t = 4m + K, upper plane pidx = t + 1 sits in ring slot (K+1)&3
+            auto step = [&](auto kc, const int t, const unsigned ph, const double (&fl)[12], double (&fn)[12], const double (&uo)[3],
+                            double (&un)[3], const unsigned mo, unsigned& mn) {
+                constexpr int K = decltype(kc)::v;
+                constexpr int S = (K + 1) & 3;                       // ring slot of plane t + 1
+                const unsigned php = (K == 3) ? (ph ^ 1u) : ph;      // its phase parity: ((t + 1) >> 2) & 1
+                mn = (innode && pfirst + t + 1 < P.nzl) ? (unsigned)*mptr : 0u;
+                mptr += P.mstride;
+                mbar_wait(&bars[S], php);
+                const double2* kz = &KB.k[0][0] + (t >> (30 - K));  // see gen-1: keeps the constant loads per-step LDCU; a different shift per sub-step so they are not merged
+                const double* su = su0 + S * (L::STAGE_BYTES / 8);
+                double* xw = xw0 + K * 6 * NT;
+
+                double ex0[3][2];
+                {
+                    face_modes(su, fn, un);
+                    const double Ee = su[L::U_BYTES / 8];
+                    double uh[3][8];
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int f = 0; f < 4; f++) {
+                            uh[c][f] = fl[4 * c + f] + fn[4 * c + f];
+                            uh[c][4 + f] = fl[4 * c + f] - fn[4 * c + f];
+                        }
+                    double yh[3][8];
+#pragma unroll
+                    for (int rho = 0; rho < 8; rho++) {
+                        const double in0 = uh[0][rho ^ 1], in1 = uh[1][rho ^ 2], in2 = uh[2][rho ^ 4];
+                        const double2 k0 = kz[rho * 3 + 0], k1 = kz[rho * 3 + 1], k2 = kz[rho * 3 + 2];
+                        const double b00 = k0.x, b01 = k0.y, b02 = k1.x, b11 = k1.y, b12 = k2.x, b22 = k2.y;
+                        double o0, o1, o2v;
+                        if (rho == 1) {
+                            o0 = 0.0;
+                            o1 = b11 * in1 + b12 * in2;
+                            o2v = b12 * in1 + b22 * in2;
+                        } else if (rho == 2) {
+                            o1 = 0.0;
+                            o0 = b00 * in0 + b02 * in2;
+                            o2v = b02 * in0 + b22 * in2;
+                        } else if (rho == 4) {
+                            o2v = 0.0;
+                            o0 = b00 * in0 + b01 * in1;
+                            o1 = b01 * in0 + b11 * in1;
+                        } else {
+                            o0 = b00 * in0 + b01 * in1 + b02 * in2;
+                            o1 = b01 * in0 + b11 * in1 + b12 * in2;
+                            o2v = b02 * in0 + b12 * in1 + b22 * in2;
+                        }
+                        yh[0][rho ^ 1] = o0;
+                        yh[1][rho ^ 2] = o1;
+                        yh[2][rho ^ 4] = o2v;
+                    }
+                    double ht[3][4];
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int f = 0; f < 4; f++) {
+                            const double sl = yh[c][f] + yh[c][4 + f], su2 = yh[c][f] - yh[c][4 + f];
+                            ht[c][f] = fma(Ee, sl, upr[4 * c + f]);
+                            upr[4 * c + f] = Ee * su2;
+                        }
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int ma = 0; ma < 2; ma++) {
+                            ex0[c][ma] = ht[c][ma] + ht[c][ma + 2];
+                            xw[(2 * c + ma) * NT] = ht[c][ma] - ht[c][ma + 2];
+                        }
+                }
+                __syncwarp();
+                if (tx == 0 && signals) mbar_arrive(&xb_mine[K]);
+                if (has_below) mbar_wait(&xb_below[K], ph);
+
+                double v[3], vr[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double e0 = ex0[c][0], e1 = ex0[c][1];
+                    if (has_below) {
+                        e0 += xw[(2 * c + 0) * NT - 32];
+                        e1 += xw[(2 * c + 1) * NT - 32];
+                    }
+                    v[c] = e0 + e1;
+                    vr[c] = e0 - e1;
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) v[c] += __shfl_up_sync(0xffffffffu, vr[c], 1);
+
+                const int e = pfirst + t;
+                if (outthr && e >= z0) {
+                    double* yp = ybase;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const bool fixed = (mo >> c) & 1u;
+                        const double au = fixed ? uo[c] : v[c];
+                        if (EPI == EPI_Y) {
+                            yp[c * P.nstride] = au;
+                        } else if (EPI == EPI_DOT) {
+                            yp[c * P.nstride] = au;
+                            part = fma(uo[c], au, part);
+                        } else if (EPI == EPI_RESID) {
+                            const double r = yp[c * P.nstride + adiff] - au;
+                            yp[c * P.nstride] = r;
+                            part = fma(r, r, part);
+                        } else {  // EPI_CHEB
+                            const long long idx = (yp - P.y) + c * P.nstride;
+                            const double r = P.a0[idx] - au;
+                            const double dn = P.s0 * P.o1[idx] + P.s1 * P.a1[idx] * r;
+                            P.o1[idx] = dn;
+                            yp[c * P.nstride] = uo[c] + dn;
+                        }
+                    }
+                }
+                ybase += P.pstride;
+                __syncwarp();
+                if (tx == 0) mbar_arrive(&ebars[S]);
+                if (MERGED) {
+                    if (refills && t + 1 + L::STAGES < nplanes) {  // every row is done with plane t + 1: refill its slot
+                        mbar_wait(&ebars[S], php);
+                        if (tx == 0) issue(t + 1 + L::STAGES);
+                    }
+                }
+            };
+
+            const int nsteps = z1 - pfirst;
+            unsigned ph = 0;
+            for (int t0 = 0; t0 < nsteps; t0 += 4, ph ^= 1u) {
+                step(IntC<0>(), t0, ph, fA, fB, uA, uB, mA, mB);
+                if (t0 + 1 >= nsteps) break;
+                step(IntC<1>(), t0 + 1, ph, fB, fA, uB, uA, mB, mA);
+                if (t0 + 2 >= nsteps) break;
+                step(IntC<2>(), t0 + 2, ph, fA, fB, uA, uB, mA, mB);
+                if (t0 + 3 >= nsteps) break;
+                step(IntC<3>(), t0 + 3, ph, fB, fA, uB, uA, mB, mA);
+            }
+        }
+    }
+    if (EPI == EPI_DOT || EPI == EPI_RESID) {
+        part = block_sum(part, red);
+        if (tid == 0) P.partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = part;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // host launch
 // ---------------------------------------------------------------------------------------
-template <int TY, int EPI, bool FLAGS>
+template <int TY, int EPI, bool FLAGS, int GEN = 1>
 static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
-    using L = ZmSmem<TY, FLAGS>;
+    constexpr int ROWS = (GEN == 3) ? TY + 1 : TY;  // node rows of the TMA box (gen 3 = gen 2 with the producer merged into the last row)
+    using L = ZmSmem<TY, FLAGS, ROWS>;
     CUtensorMap tmU, tmE;
     {
         cuuint64_t dims[4] = {(cuuint64_t)g.nxn, (cuuint64_t)g.nyn, 3, (cuuint64_t)g.nzl()};
         cuuint64_t str[3] = {(cuuint64_t)g.px * 8, (cuuint64_t)g.nstride * 8, (cuuint64_t)g.pstride * 8};
-        cuuint32_t box[4] = {ZM_W, (cuuint32_t)TY, 3, 1};
+        cuuint32_t box[4] = {ZM_W, (cuuint32_t)ROWS, 3, 1};
         TOB_CHECK(encode_map(c, &tmU, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, a.u, dims, str, box));
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)g.nex, (cuuint64_t)g.ney, (cuuint64_t)g.nzle()};
         cuuint64_t str[2] = {(cuuint64_t)g.pe * 8, (cuuint64_t)g.estride * 8};
-        cuuint32_t box[3] = {ZM_W, (cuuint32_t)TY, 1};
+        cuuint32_t box[3] = {ZM_W, (cuuint32_t)ROWS, 1};
         TOB_CHECK(encode_map(c, &tmE, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, a.E, dims, str, box));
     }
     ZmParams P;
@@ -515,7 +782,7 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1();
     P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
     P.l2hint = a.l2hint;
-    const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, TY - 2);
+    const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, ROWS - 2);
     const int nz = P.zout1 - P.zout0;
     // z-chunks: every chunk recomputes one element layer and pays a prologue, and the grid runs in waves
     // of ctas_per_wave CTAs (ncu: with 3.16 waves the SMs idled 21% of the time) -> pick the chunk count
@@ -537,11 +804,15 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
     if ((long long)gx * gy * nch > kMaxPartials) TOB_FAIL("grid too large for the partial-sum buffer");
-    auto kern = k_hex8_zmarch<TY, EPI, FLAGS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    void (*kern)(const CUtensorMap, const CUtensorMap, const Hex8BlocksPacked, const ZmParams);
+    if constexpr (GEN == 2) kern = k_hex8_zm4<TY, EPI, false>;
+    else if constexpr (GEN == 3) kern = k_hex8_zm4<TY, EPI, true>;
+    else kern = k_hex8_zmarch<TY, EPI, FLAGS>;
+    // the opt-in is per device (a process may hold contexts on several devices): cheap, so set it on every launch path once per device
+    static bool attr_set[64] = {};
+    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
         TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
+        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
     }
     Hex8BlocksPacked kp;
     for (int rho = 0; rho < 8; rho++) {
@@ -557,13 +828,13 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     return 0;
 }
 
-template <int TY, bool FLAGS>
+template <int TY, bool FLAGS, int GEN = 1>
 static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts) {
     switch (a.epi) {
-        case EPI_Y: return launch_zm<TY, EPI_Y, FLAGS>(c, g, op, a, nparts);
-        case EPI_DOT: return launch_zm<TY, EPI_DOT, FLAGS>(c, g, op, a, nparts);
-        case EPI_RESID: return launch_zm<TY, EPI_RESID, FLAGS>(c, g, op, a, nparts);
-        default: return launch_zm<TY, EPI_CHEB, FLAGS>(c, g, op, a, nparts);
+        case EPI_Y: return launch_zm<TY, EPI_Y, FLAGS, GEN>(c, g, op, a, nparts);
+        case EPI_DOT: return launch_zm<TY, EPI_DOT, FLAGS, GEN>(c, g, op, a, nparts);
+        case EPI_RESID: return launch_zm<TY, EPI_RESID, FLAGS, GEN>(c, g, op, a, nparts);
+        default: return launch_zm<TY, EPI_CHEB, FLAGS, GEN>(c, g, op, a, nparts);
     }
 }
 
@@ -588,6 +859,8 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
     if (kernel == SPMV_ZM16 || kernel == SPMV_ZM16R) return dispatch_zm<16, false>(c, g, op, a, nparts);
     if (kernel == SPMV_ZM12) return dispatch_zm<12, false>(c, g, op, a, nparts);
     if (kernel == SPMV_ZM8RF) return dispatch_zm<8, true>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16U4) return dispatch_zm<16, true, 2>(c, g, op, a, nparts);
+    if (kernel == SPMV_ZM16M4) return dispatch_zm<16, true, 3>(c, g, op, a, nparts);
     if (kernel == SPMV_ZM16RF) return dispatch_zm<16, true>(c, g, op, a, nparts);
     if (kernel == SPMV_ZM12RF) return dispatch_zm<12, true>(c, g, op, a, nparts);
     return dispatch_zm<8, false>(c, g, op, a, nparts);  // SPMV_ZM8, SPMV_ZM8R

@@ -26,7 +26,7 @@ int hex8_build_operator(double dx, double dy, double dz, double nu, Hex8Operator
 void hex8_free_operator(Hex8Operator& op);
 
 enum SpmvEpilogue { EPI_Y = 0, EPI_DOT = 1, EPI_RESID = 2, EPI_CHEB = 3 };
-enum SpmvKernel { SPMV_AUTO = 0, SPMV_NAIVE = 1, SPMV_ZM8 = 2, SPMV_ZM16 = 3, SPMV_ZM12 = 4, SPMV_ZM8R = 5, SPMV_ZM8RF = 6, SPMV_ZM16RF = 7, SPMV_ZM12RF = 8, SPMV_ZM16R = 9 };
+enum SpmvKernel { SPMV_AUTO = 0, SPMV_NAIVE = 1, SPMV_ZM8 = 2, SPMV_ZM16 = 3, SPMV_ZM12 = 4, SPMV_ZM8R = 5, SPMV_ZM8RF = 6, SPMV_ZM16RF = 7, SPMV_ZM12RF = 8, SPMV_ZM16R = 9, SPMV_ZM16U4 = 10, SPMV_ZM16M4 = 11 };
 
 struct SpmvArgs {
     const double* u = nullptr;           // stored nodal vector (ghost planes already exchanged)
