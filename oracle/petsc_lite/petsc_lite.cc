@@ -38,6 +38,7 @@ struct _p_Mat {
     }
     void apply(const PetscScalar* x, PetscScalar* y) {
         csr();
+#pragma omp parallel for schedule(static)
         for (PetscInt i = 0; i < m; i++) {
             PetscScalar s = 0;
             for (PetscInt k = rp[(size_t)i]; k < rp[(size_t)i + 1]; k++) s += va[(size_t)k] * x[ci[(size_t)k]];
@@ -568,6 +569,8 @@ PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
     bnorm = sqrt(bnorm);
     apply(x->a, q.data());
     PetscReal rz = 0, rr = 0;
+    // (the loops below run under OpenMP when the build enables it: long fixture runs, tests/golden/make_trajectory_golden.py)
+#pragma omp parallel for schedule(static) reduction(+ : rz, rr)
     for (PetscInt i = 0; i < n; i++) {
         r[(size_t)i] = b->a[i] - q[(size_t)i];
         z[(size_t)i] = dinv[(size_t)i] * r[(size_t)i];
@@ -580,11 +583,13 @@ PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
     while (sqrt(rr) > tol && it < 200000) {
         apply(p.data(), q.data());
         PetscReal pq = 0;
+#pragma omp parallel for schedule(static) reduction(+ : pq)
         for (PetscInt i = 0; i < n; i++) pq += p[(size_t)i] * q[(size_t)i];
         if (!(pq > 0)) break;
         const PetscReal alpha = rz / pq;
         PetscReal rz_new = 0;
         rr = 0;
+#pragma omp parallel for schedule(static) reduction(+ : rz_new, rr)
         for (PetscInt i = 0; i < n; i++) {
             x->a[i] += alpha * p[(size_t)i];
             r[(size_t)i] -= alpha * q[(size_t)i];
@@ -594,6 +599,7 @@ PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
         }
         const PetscReal beta = rz_new / rz;
         rz = rz_new;
+#pragma omp parallel for schedule(static)
         for (PetscInt i = 0; i < n; i++) p[(size_t)i] = z[(size_t)i] + beta * p[(size_t)i];
         it++;
     }

@@ -48,6 +48,17 @@ fx, gx = phys.ComputeObjectiveConstraintsSensitivities(df, dg, x[e0:e1].copy(), 
 assert abs(fx - fx0) <= 1e-7 * abs(fx0) and abs(gx - gx0) <= 1e-12, ("obj", fx, fx0)
 assert np.abs(df - df0[e0:e1]).max() <= 1e-6 * np.abs(df0).max(), "sens"
 assert np.abs(phys.GetStateField() - U[d0:d1]).max() <= 1e-6 * np.abs(U).max(), "state"
+# single-reduction Jacobi-PCG (cgsr.cuh; the default on several ranks for rtol >= 1e-8): halo planes stored by the
+# neighbours' update kernels, sums published by the last CTA of the SpMV
+psr = LinearElasticity(ctx, opts=solver_opts(rtol=1e-8, maxits=50000, check_every=10))
+ssr = psr.SolveState(x[e0:e1].copy(), 1e-9, 1.0, 3.0)
+assert ssr.rel_residual <= 1e-8 and ssr.iterations > 10, ("sr-pcg", ssr.rel_residual, ssr.iterations)
+assert np.abs(psr.GetStateField() - U[d0:d1]).max() <= 1e-5 * np.abs(U).max(), "sr-pcg state"
+ssr2 = psr.SolveState((0.8 * x[e0:e1] + 0.1).copy(), 1e-9, 1.0, 3.0)  # second solve: replays the graph, epochs continue
+assert ssr2.rel_residual <= 1e-8
+if rank == 0:
+    print("sr-pcg iterations", ssr.iterations, ssr2.iterations, flush=True)
+psr.close()
 # filter (2-cell radius so ghost layers matter)
 fo = o.FilterOracle(g, 1, 0.25)
 flt = Filter(ctx, 1, 0.25)

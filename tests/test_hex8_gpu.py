@@ -243,3 +243,138 @@ def test_error_paths():
     with pytest.raises(TobError):
         f.GetHs()
     f.close(); phys.close(); ctx.close()
+
+
+# ---- BASELINE configs[1] size: the default kernel's z-chunking, wave logic and (in the solver) L2 hints engage here -------
+def _spmv_matrix_free_fast(oracle, g, KE, E, N, u):
+    """oracle.spmv_matrix_free with the scatter done by bincount (np.add.at takes minutes at 1.8 M elements)."""
+    ed = g.edof()
+    ye = ((N * u)[ed] @ KE.T) * E[:, None]
+    y = np.bincount(ed.ravel(), weights=ye.ravel(), minlength=g.ndof)
+    return N * y + (1.0 - N) * u
+
+
+@pytest.mark.parametrize("dens", ["uniform", "random", "checker"])
+def test_spmv_parity_cfg2_size(oracle, dens):
+    """193 x 97 x 97 nodes (BASELINE configs[1]): default SpMV kernel and diag(K) vs the numpy oracle, <= 1e-12 relative."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity
+    rng = np.random.default_rng(1234)
+    shape = (193, 97, 97)
+    g = oracle.Grid(*shape)
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N, _ = oracle.cantilever_bc_load(g)
+    x = densities(dens, g, rng)
+    E = oracle.simp_modulus(x, 1e-9, 1.0, 3.0)
+    u = rng.uniform(-1, 1, g.ndof)
+    # small-grid check of the fast scatter against the oracle's own function
+    gs = oracle.Grid(9, 5, 5)
+    us, Es = rng.uniform(-1, 1, gs.ndof), rng.uniform(0, 1, gs.nel)
+    Ns, _ = oracle.cantilever_bc_load(gs)
+    KEs = oracle.hex8_ke(gs.dx, gs.dy, gs.dz, 0.3)
+    assert np.abs(_spmv_matrix_free_fast(oracle, gs, KEs, Es, Ns, us) - oracle.spmv_matrix_free(gs, KEs, Es, Ns, us)).max() < 1e-13
+    yref = _spmv_matrix_free_fast(oracle, g, KE, E, N, u)
+    ctx = Context(*shape)
+    assert ctx.nel == g.nel == 1769472 and ctx.ndof == g.ndof == 5447811
+    phys = LinearElasticity(ctx, nu=0.3)
+    phys.SetDensity(x, 1e-9, 1.0, 3.0)
+    y = phys.SpMV(u)
+    assert np.abs(y - yref).max() <= 1e-12 * np.abs(yref).max()
+    # diag(K) = KE_cc * sum of the 8 adjacent moduli on free dofs, 1 on clamped ones (LinearElasticity.cc:510-538)
+    ed = g.edof()
+    dref = np.bincount(ed.ravel(), weights=(E[:, None] * np.diag(KE)[None, :]).ravel(), minlength=g.ndof)
+    dref = N * dref + (1.0 - N)
+    assert np.abs(phys.Diag() - dref).max() <= 1e-13 * dref.max()
+    phys.close(); ctx.close()
+
+
+def test_iteration1_compliance_cfg2_vs_cpu_reference_solver():
+    """Iteration-1 compliance of BASELINE configs[1] (192x96x96, uniform 0.12): the product's Jacobi-PCG (default kernel,
+    L2 hints and CUDA-graphed iterations on) and its multigrid-PCG, both to 1e-10, against the C restatement of the
+    reference's FGMRES + Galerkin-PCMG solver on the assembled CSR matrix (oracle/c/cpu_ref.c), also to 1e-10.
+    Compliance error is second order in the residual -> 1e-8 relative."""
+    import cpu_ref
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    shape = (193, 97, 97)
+    ctx = Context(*shape)
+    x = np.full(ctx.nel, 0.12)
+    dfdx, dgdx = np.empty(ctx.nel), np.empty(ctx.nel)
+    res = {}
+    for name, opts in (("jacobi", solver_opts(pc=0, rtol=1e-10, maxits=200000, check_every=50)),
+                       ("gmg", solver_opts(pc=1, nlvls=6, rtol=1e-10, maxits=500, cheb_degree=3, coarse_its=20))):
+        phys = LinearElasticity(ctx, opts=opts)
+        fx, gx = phys.ComputeObjectiveConstraintsSensitivities(dfdx, dgdx, x, 1e-9, 1.0, 3.0, 0.12)
+        st = phys.stats()
+        assert st.rel_residual <= 1e-10
+        res[name] = (fx, dfdx.copy(), st.iterations)
+        phys.close()
+    ctx.close()
+    cr = cpu_ref.CpuRef(*shape, nthreads=os.cpu_count())
+    cr.assemble(x)
+    cr.mg_setup(4)
+    U, its, rel, _ = cr.fgmres_mg(rtol=1e-10, maxits=200)
+    assert rel <= 1e-10
+    fx0, gx0, df0, _ = cr.objective(U, x)
+    cr.close()
+    print(f"cfg2 iteration 1: cpu fx={fx0:.12g} ({its} FGMRES its), jacobi {res['jacobi'][0]:.12g} ({res['jacobi'][2]} its), "
+          f"gmg {res['gmg'][0]:.12g} ({res['gmg'][2]} its)")
+    for name in res:
+        assert abs(res[name][0] - fx0) <= 1e-8 * fx0, name
+        assert np.abs(res[name][1] - df0).max() <= 1e-6 * np.abs(df0).max(), name
+
+
+def test_split_objective_and_sensitivity_entry_points(oracle):
+    """ComputeObjectiveConstraints (LinearElasticity.cc:225-297) and ComputeSensitivities (:299-361) through
+    tob_elast_obj / tob_elast_sens give what the fused call gives, and what the oracle gives."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(11)
+    shape = (21, 11, 9)
+    g = oracle.Grid(*shape)
+    x = 0.05 + 0.9 * rng.uniform(0, 1, g.nel)
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N, RHS = oracle.cantilever_bc_load(g)
+    K = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N)
+    U = spla.spsolve(K.tocsc(), N * RHS)
+    fx0, gx0, df0, dg0 = oracle.objective_sens(g, KE, U, x, 1e-9, 1.0, 3.0, 0.3)
+    ctx = Context(*shape)
+    phys = LinearElasticity(ctx, opts=solver_opts(rtol=1e-12, maxits=50000))
+    fx, gx = phys.ComputeObjectiveConstraints(x, 1e-9, 1.0, 3.0, 0.3)
+    assert abs(fx - fx0) <= 1e-8 * fx0 and abs(gx - gx0) <= 1e-13
+    dfdx, dgdx = np.empty(g.nel), np.empty(g.nel)
+    phys.ComputeSensitivities(dfdx, dgdx, x, 1e-9, 1.0, 3.0, 0.3)  # reuses the state of the solve above (:317-318)
+    assert np.abs(dfdx - df0).max() <= 1e-7 * np.abs(df0).max()
+    assert np.allclose(dgdx, dg0, rtol=0, atol=1e-18)
+    d2, g2 = np.empty(g.nel), np.empty(g.nel)
+    fx2, gx2 = phys.ComputeObjectiveConstraintsSensitivities(d2, g2, x, 1e-9, 1.0, 3.0, 0.3)
+    assert abs(fx2 - fx) <= 1e-12 * fx and gx2 == gx and np.abs(d2 - dfdx).max() <= 1e-12 * np.abs(dfdx).max()
+    phys.close(); ctx.close()
+
+
+@pytest.mark.parametrize("dens", ["uniform", "random"])
+def test_single_reduction_pcg_on_one_rank(oracle, dens, monkeypatch):
+    """The Chronopoulos-Gear Jacobi-PCG (cgsr.cuh: 2 launches per iteration, sums published by the SpMV's last CTA), forced
+    on one rank with TOB_PCG_SR=1, converges to the same state as a direct solve; iteration count close to classical PCG."""
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    import scipy.sparse.linalg as spla
+    rng = np.random.default_rng(5)
+    shape = (33, 17, 17)
+    g = oracle.Grid(*shape)
+    x = densities(dens, g, rng)
+    x = 0.05 + 0.9 * x if dens == "random" else x
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N, RHS = oracle.cantilever_bc_load(g)
+    U = spla.spsolve(oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N).tocsc(), N * RHS)
+    ctx = Context(*shape)
+    monkeypatch.setenv("TOB_PCG_SR", "0")
+    cl = LinearElasticity(ctx, opts=solver_opts(rtol=1e-8, maxits=50000, check_every=10))
+    s0 = cl.SolveState(x, 1e-9, 1.0, 3.0)
+    monkeypatch.setenv("TOB_PCG_SR", "1")
+    sr = LinearElasticity(ctx, opts=solver_opts(rtol=1e-8, maxits=50000, check_every=10))
+    s1 = sr.SolveState(x, 1e-9, 1.0, 3.0)
+    print(f"[{dens}] classical its={s0.iterations} single-reduction its={s1.iterations}")
+    assert s1.rel_residual <= 1e-8
+    assert s1.iterations <= 1.15 * s0.iterations + 24
+    assert np.abs(sr.GetStateField() - U).max() <= 1e-5 * np.abs(U).max()
+    s2 = sr.SolveState(0.9 * x + 0.05, 1e-9, 1.0, 3.0)  # warm-started second solve through the captured graph
+    assert s2.rel_residual <= 1e-8
+    cl.close(); sr.close(); ctx.close()

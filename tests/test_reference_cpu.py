@@ -67,7 +67,8 @@ def test_reference_binary_reproduces_fixture_and_container_layout(tmp_path):
     assert G.parse_history(stdout) == c["history"]
     vecs = G.read_petsc_vecs(os.path.join(d, "Restart00.dat"))
     assert len(vecs) == 6  # x, xPhys, xo1, xo2, U(asymptote), L(asymptote): TopOpt.cc:556-562
-    assert np.array_equal(vecs[0][::c["stride"]], np.array(c["x"]))
+    # (petsc_lite's exact solve sums under OpenMP: the last bits depend on the thread count, nothing else does)
+    assert np.abs(vecs[0][::c["stride"]] - np.array(c["x"])).max() <= 1e-11
     # result container written by the reference's MPIIO.cc through petsc_lite's MPI_File: the reader the GPU tests use
     # for the product's container (tests/test_dropin_gpu.py::parse_container) must read it too
     sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,0 +1,163 @@
+// cgsr.cu -- the vector-update kernel of the single-reduction Jacobi-PCG (see cgsr.cuh) and peer-mapped vectors.
+#include "cgsr.cuh"
+#include "vecops.cuh"
+
+namespace tob {
+
+__device__ __forceinline__ unsigned long long cg_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cg_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kFlatThreads)
+k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __restrict__ r, double* __restrict__ u,
+            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s, const double* __restrict__ dinv, long long n,
+            long long plane, double* __restrict__ upart, const __grid_constant__ CgPeers pe, size_t red_off0, size_t red_off1) {
+    __shared__ double red[32];
+    __shared__ double sh[2];
+    const CgState st = cg->st[par];
+    double alpha = 0.0, beta = 0.0;
+    if (MODE == 1) {
+        if (threadIdx.x == 0) {
+            double gam, rr, del;
+            if (pe.n > 1) {
+                // the three sums of every rank were stored into my arena by the last CTA of that rank's SpMV
+                const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pe.arena);
+                for (int k = 0; k < pe.n; k++)
+                    while (cg_ld_acquire_sys(&flags[F_CG_RED0 + k]) < st.epoch) {}
+                const size_t off = (st.epoch & 1) ? red_off1 : red_off0;
+                gam = rr = del = 0.0;
+                for (int k = 0; k < pe.n; k++) {  // rank order: bitwise identical on every rank
+                    const double* v = reinterpret_cast<const double*>(pe.arena + off + (size_t)k * 128 * 8) + kCgSlot;
+                    gam += __ldcg(v); rr += __ldcg(v + 1); del += __ldcg(v + 2);
+                }
+            } else {
+                gam = cg->sums[0]; rr = cg->sums[1]; del = cg->sums[2];
+            }
+            double a, b;
+            if (st.first != 0.0) { b = 0.0; a = gam / del; }
+            else { b = gam / st.gam_prev; a = gam / (del - b * gam / st.alpha_prev); }
+            sh[0] = a; sh[1] = b;
+            if (blockIdx.x == 0) {
+                cg->st[par ^ 1].gam_prev = gam; cg->st[par ^ 1].alpha_prev = a; cg->st[par ^ 1].first = 0.0;
+                cg->st[par ^ 1].epoch = st.epoch + 1;
+                cg->out[0] = gam; cg->out[1] = rr; cg->out[2] = del; cg->out[3] = a;
+            }
+        }
+        __syncthreads();
+        alpha = sh[0]; beta = sh[1];
+    } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cg->st[par ^ 1].gam_prev = 1.0; cg->st[par ^ 1].alpha_prev = 1.0; cg->st[par ^ 1].first = 1.0;
+        cg->st[par ^ 1].epoch = st.epoch + 1;
+    }
+    const unsigned long long e = st.epoch + 1;
+    const long long n2 = n >> 1, plane2 = plane >> 1;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    double2* u2 = reinterpret_cast<double2*>(u);
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* s2 = reinterpret_cast<double2*>(s);
+    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    double2* lo2 = reinterpret_cast<double2*>(pe.u_lo_ghost);
+    double2* hi2 = reinterpret_cast<double2*>(pe.u_hi_ghost);
+    double gam = 0.0, rr = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 rv = r2[i];
+        if (MODE == 1) {
+            const double2 uv = u2[i], wv = w2[i];
+            double2 pv = p2[i], sv = s2[i], xv = x2[i];
+            pv.x = fma(beta, pv.x, uv.x); pv.y = fma(beta, pv.y, uv.y);
+            sv.x = fma(beta, sv.x, wv.x); sv.y = fma(beta, sv.y, wv.y);
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            rv.x = fma(-alpha, sv.x, rv.x); rv.y = fma(-alpha, sv.y, rv.y);
+            p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv;
+        }
+        const double2 dv = d2[i];
+        const double2 un = make_double2(dv.x * rv.x, dv.y * rv.y);
+        u2[i] = un;
+        if (lo2 && i < plane2) lo2[i] = un;                              // my first owned plane = lower neighbour's top ghost
+        if (hi2 && i >= n2 - plane2) hi2[i - (n2 - plane2)] = un;        // my last owned plane = upper neighbour's bottom ghost
+        gam = fma(rv.x, un.x, gam); gam = fma(rv.y, un.y, gam);
+        rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
+    }
+    if (pe.n > 1) __threadfence_system();
+    gam = block_sum(gam, red);
+    rr = block_sum(rr, red);
+    if (threadIdx.x == 0) {
+        upart[blockIdx.x] = gam;
+        upart[gridDim.x + blockIdx.x] = rr;
+        if (pe.n > 1) {
+            __threadfence();
+            const unsigned int done = atomicAdd(&cg->ucounter, 1u) + 1u;
+            if (done == gridDim.x) {  // every block of this launch has pushed its share of the boundary planes
+                cg->ucounter = 0u;
+                __threadfence_system();
+                if (pe.rank > 0) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank - 1]) + F_CG_FROM_HI, e);
+                if (pe.rank < pe.n - 1) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank + 1]) + F_CG_FROM_LO, e);
+            }
+        }
+    }
+}
+
+int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, double* r, double* u, const double* w,
+              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers) {
+    const int nb = flat_grid(c, g.own_len);
+    const long long o = g.own_off;
+    const size_t r0 = peers.n > 1 ? cg_red_off(peers.n, 0, 0) : 0, r1 = peers.n > 1 ? cg_red_off(peers.n, 1, 0) : 0;
+    if (mode == 0)
+        k_cg_update<0><<<nb, kFlatThreads, 0, c->stream>>>(cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride,
+                                                         upart, peers, r0, r1);
+    else
+        k_cg_update<1><<<nb, kFlatThreads, 0, c->stream>>>(cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride,
+                                                         upart, peers, r0, r1);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    if (nbU) *nbU = nb;
+    return 0;
+}
+
+// ---- peer-mapped vectors ---------------------------------------------------------------------------------------------------
+int peer_vec_alloc(tob_ctx_impl* c, size_t nbytes, PeerVec* out) {
+    const int n = c->desc.nranks, r = c->desc.rank;
+    *out = PeerVec();
+    out->bytes = nbytes;
+    TOB_CUDA(cudaMalloc(&out->mine, nbytes));
+    TOB_CUDA(cudaMemsetAsync(out->mine, 0, nbytes, c->stream));
+    out->peer[r] = out->mine;
+    if (n == 1) return 0;
+    cudaIpcMemHandle_t mine;
+    TOB_CUDA(cudaIpcGetMemHandle(&mine, out->mine));
+    unsigned char* d_all = nullptr;
+    TOB_CUDA(cudaMalloc(&d_all, sizeof(mine) * n));
+    TOB_CUDA(cudaMemcpyAsync(d_all + sizeof(mine) * r, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    TOB_NCCL(ncclAllGather(d_all + sizeof(mine) * r, d_all, sizeof(mine), ncclUint8, c->comm, c->stream));
+    TOB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<cudaIpcMemHandle_t> all(n);
+    TOB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(mine) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    // only the z-neighbours' buffers are needed (and IPC mappings are not free): open those two
+    for (int k = r - 1; k <= r + 1; k += 2) {
+        if (k < 0 || k >= n) continue;
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) TOB_FAIL(std::string("cudaIpcOpenMemHandle (peer vector): ") + cudaGetErrorString(e));
+        out->peer[k] = (double*)p;
+    }
+    return 0;
+}
+
+void peer_vec_free(tob_ctx_impl* c, PeerVec* v) {
+    if (!v->mine) return;
+    for (int k = 0; k < c->desc.nranks; k++)
+        if (k != c->desc.rank && v->peer[k]) cudaIpcCloseMemHandle(v->peer[k]);
+    cudaFree(v->mine);
+    *v = PeerVec();
+}
+
+}  // namespace tob

@@ -1,0 +1,57 @@
+// cgsr.cuh -- single-reduction (Chronopoulos-Gear) Jacobi-PCG: the multi-GPU Krylov iteration as TWO launches.
+//
+// Classical PCG needs two global reductions per iteration (p.Ap, then r.z), each a cross-GPU round trip on the critical
+// path; with the halo exchange that was 6 launches and 3 flag round trips per iteration (round 1: 65 us per iteration on
+// 8 GPUs for 25 us of kernel time).  The Chronopoulos-Gear recurrence carries s = A p along, so both inner products of an
+// iteration are available after ONE operator application:
+//     U:  [alpha, beta from last iteration's sums]   p = u + beta p ;  s = w + beta s ;  x += alpha p ;  r -= alpha s ;
+//         u = D^-1 r  (also stored straight into the neighbours' ghost planes over NVLink) ;  partials of r.u and r.r
+//     S:  w = A u  (z-march SpMV; only the CTAs that touch a ghost plane wait for the neighbour's flag) ; partials of w.u ;
+//         the LAST CTA to finish sums all partials, stores the three sums into every peer's arena and raises a flag.
+// The next U spins on the peers' flags and adds the per-rank sums in rank order (bitwise identical on all ranks).
+// No halo kernel, no finalize kernels: 2 launches and 2 NVLink latencies per iteration.
+#pragma once
+#include "common.cuh"
+
+namespace tob {
+
+struct CgState {  // ping-pong: U reads st[par], writes st[par ^ 1]
+    double gam_prev, alpha_prev, first;
+    unsigned long long epoch;  // number of U launches so far on this context (monotone: the cross-GPU flag value)
+};
+struct CgDev {
+    CgState st[2];
+    double sums[3];         // single rank: r.u, r.r, w.u of the last (U, S) pair
+    unsigned int ucounter;  // "last CTA" tickets of U (halo flags) and S (reduction)
+    unsigned int scounter;
+    double out[4];          // for the host: r.u, r.r, w.u, alpha
+};
+
+// u64 indices in the arena flag page used by this path (comm.cu owns indices < 40)
+enum { F_CG_FROM_LO = 40, F_CG_FROM_HI = 41, F_CG_RED0 = 64 };
+constexpr int kCgSlot = 120;  // doubles 120..122 of a reduction slot carry the three sums
+
+struct CgPeers {  // per-launch description of the neighbourhood (by value in the kernel parameters)
+    int n = 1, rank = 0;
+    unsigned char* arena = nullptr;         // my arena (flags + reduction slots)
+    unsigned char* peer[kMaxRanks] = {};    // every rank's arena
+    double* u_lo_ghost = nullptr;           // lower neighbour's TOP ghost plane of u (null if none)
+    double* u_hi_ghost = nullptr;           // upper neighbour's BOTTOM ghost plane of u
+};
+
+size_t cg_red_off(int n, int parity, int rank);  // byte offset of a reduction slot inside an arena (comm.cu)
+
+// peer-mapped vector: cudaMalloc + IPC handle exchange (collective).  peer[k] = rank k's buffer in this address space.
+struct PeerVec {
+    double* mine = nullptr;
+    double* peer[kMaxRanks] = {};
+    size_t bytes = 0;
+};
+int peer_vec_alloc(tob_ctx_impl* c, size_t nbytes, PeerVec* out);
+void peer_vec_free(tob_ctx_impl* c, PeerVec* v);
+
+// U kernel.  mode 0 = set-up (u = dinv r only, first = 1), mode 1 = iteration.  par = parity of the state it reads.
+int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, double* r, double* u, const double* w,
+              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers);
+
+}  // namespace tob

@@ -14,6 +14,7 @@
 //  * NCCL (set-up traffic, wide element-field halos of the cone filter, and everything when TOB_P2P=0).
 #include "common.cuh"
 #include "vecops.cuh"
+#include "cgsr.cuh"
 
 namespace tob {
 
@@ -38,6 +39,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 
 __device__ __forceinline__ size_t red_off(int n, int parity, int rank) { return kFlagBytes + ((size_t)(parity * n + rank) * kRedSlots) * 8; }
+size_t cg_red_off(int n, int parity, int rank) { return kFlagBytes + ((size_t)(parity * n + rank) * kRedSlots) * 8; }  // == red_off (cgsr.cuh)
 static size_t zone_off(int n, size_t plane_bytes, int parity, int dir) {
     return kFlagBytes + (size_t)2 * n * kRedSlots * 8 + (size_t)(parity * 2 + dir) * plane_bytes;
 }
@@ -165,19 +167,41 @@ int peer_setup(tob_ctx_impl* c, size_t plane_bytes) {
     std::vector<cudaIpcMemHandle_t> all(n);
     TOB_CUDA(cudaMemcpy(all.data(), d_all, sizeof(mine) * n, cudaMemcpyDeviceToHost));
     cudaFree(d_all);
+    // Open every peer's arena; the decision to use the peer transport is COLLECTIVE (a rank that cannot map a peer must not
+    // leave the others spinning on flags it will never write): all-reduce(min) of the local outcome over NCCL.
+    int ok_local = 1;
+    cudaError_t first_err = cudaSuccess;
     for (int k = 0; k < n; k++) {
         if (k == r) { pc.peer[k] = pc.arena; continue; }
         void* p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, all[k], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            if (c->desc.rank == 0) fprintf(stderr, "libtopopt_b200: CUDA IPC peer access unavailable (%s); using NCCL for halos\n", cudaGetErrorString(e));
-            for (int j = 0; j < k; j++) if (j != r && pc.peer[j]) cudaIpcCloseMemHandle(pc.peer[j]);
+            if (ok_local) first_err = e;
+            ok_local = 0;
+            pc.peer[k] = nullptr;
+            continue;
+        }
+        pc.peer[k] = (unsigned char*)p;
+    }
+    {
+        int* d_ok = nullptr;
+        TOB_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+        TOB_CUDA(cudaMemcpy(d_ok, &ok_local, sizeof(int), cudaMemcpyHostToDevice));
+        TOB_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream));
+        TOB_CUDA(cudaStreamSynchronize(c->stream));
+        int ok_all = 0;
+        TOB_CUDA(cudaMemcpy(&ok_all, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_ok);
+        if (!ok_all) {
+            if (!ok_local || r == 0)
+                fprintf(stderr, "libtopopt_b200[rank %d]: CUDA IPC peer access unavailable on %s (%s); every rank uses NCCL for halos\n", r,
+                        ok_local ? "another rank" : "this rank", ok_local ? "-" : cudaGetErrorString(first_err));
+            for (int j = 0; j < n; j++) if (j != r && pc.peer[j]) cudaIpcCloseMemHandle(pc.peer[j]);
             cudaFree(pc.arena);
             pc = PeerComm();
             return 0;
         }
-        pc.peer[k] = (unsigned char*)p;
     }
     pc.enabled = true;
     // nobody may touch a peer arena before every rank has zeroed its own
@@ -268,7 +292,7 @@ int allgatherv_bytes(tob_ctx_impl* c, const void* mine, void* dst, const size_t*
 static int allreduce(tob_ctx_impl* c, double* d_vals, int n, int op) {
     if (c->desc.nranks == 1) return 0;
     PeerComm& pc = c->peer;
-    if (pc.enabled && n <= (int)kRedSlots) {
+    if (pc.enabled && n <= kCgSlot) {  // doubles kCgSlot.. of a slot belong to the single-reduction PCG (cgsr.cuh)
         PeerPtrs pp;
         for (int k = 0; k < kMaxRanks; k++) pp.p[k] = k < c->desc.nranks ? pc.peer[k] : nullptr;
         k_finalize_p2p<<<1, 256, 0, c->stream>>>(nullptr, 0, d_vals, n, op, c->desc.nranks, c->desc.rank, pc.arena, pp);
@@ -285,7 +309,7 @@ int allreduce_max(tob_ctx_impl* c, double* d_vals, int n) { return allreduce(c, 
 // per-CTA partials -> d_out, all-reduced: one launch on the peer path
 int finalize_allreduce(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, int op) {
     PeerComm& pc = c->peer;
-    if (c->desc.nranks > 1 && pc.enabled && nvals <= (int)kRedSlots) {
+    if (c->desc.nranks > 1 && pc.enabled && nvals <= kCgSlot) {
         PeerPtrs pp;
         for (int k = 0; k < kMaxRanks; k++) pp.p[k] = k < c->desc.nranks ? pc.peer[k] : nullptr;
         k_finalize_p2p<<<1, 256, 0, c->stream>>>(c->d_partials, nblocks, d_out, nvals, op, c->desc.nranks, c->desc.rank, pc.arena, pp);

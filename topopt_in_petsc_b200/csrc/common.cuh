@@ -121,6 +121,7 @@ struct tob_ctx_impl {
     // Measured on cfg2 (profiles/r01_l2hint_ab.txt): 0 -> 4.38, 1 -> 4.45, 3 -> 4.60, 7 -> 4.23 design it/s; with the
     // set-aside (8) 3.2-4.5: the default is 3.
     int l2hint = 3;
+    unsigned long long cg_epoch = 0;  // U launches of the single-reduction PCG so far (= the cross-GPU flag value, cgsr.cuh)
     DevBuf stage[8];  // staging buffers for host<->device vectors
     // TMA encode entry point
     void* encode_tiled = nullptr;

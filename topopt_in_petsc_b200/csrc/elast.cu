@@ -32,6 +32,10 @@ int elast_apply(tob_elast_impl* h, const double* u, double* y, int epi, bool mas
     a.a0 = a0;
     // Jacobi-PCG on one rank: working set >> L2, see common.cuh (the smaller per-rank sets of N > 1 mostly fit)
     if (epi == EPI_DOT && h->opts.pc == 0 && h->c->desc.nranks == 1) a.l2hint = h->c->l2hint;
+    if (epi == EPI_CGDOT) {
+        a.cg = h->sr_cg; a.cgpar = h->sr_par; a.upart = h->sr_upart; a.nbU = h->sr_nbU; a.pe = &h->sr_pe;
+        if (h->c->desc.nranks == 1) a.l2hint = h->c->l2hint & 1;  // modulus tiles evict_first
+    }
     h->stats.spmv_calls++;
     constexpr int kMaxPairs = 2048;
     // profiling mode 1 times every launch, mode >1 every mode-th launch (event pairs around every launch cost ~6 %
@@ -87,6 +91,123 @@ int elast_set_density(tob_elast_impl* h, const double* xphys_nat_dev, double Emi
     return 0;
 }
 
+
+// ---- single-reduction Jacobi-PCG (cgsr.cuh): 2 launches per iteration, one reduction, halo fused into the producer ------
+static int sr_setup(tob_elast_impl* h) {
+    tob_ctx_impl* c = h->c;
+    const LevelGrid& g = *h->g;
+    if (h->sr_cg) return 0;
+    TOB_CHECK(peer_vec_alloc(c, sizeof(double) * g.nvec, &h->sr_u));
+    TOB_CUDA(cudaMalloc(&h->sr_cg, sizeof(CgDev)));
+    TOB_CUDA(cudaMemsetAsync(h->sr_cg, 0, sizeof(CgDev), c->stream));
+    TOB_CUDA(cudaMalloc(&h->sr_upart, sizeof(double) * 2 * (size_t)c->num_sms * 8));
+    CgPeers& pe = h->sr_pe;
+    pe = CgPeers();
+    pe.n = c->desc.nranks; pe.rank = c->desc.rank;
+    if (pe.n > 1) {
+        pe.arena = c->peer.arena;
+        for (int k = 0; k < pe.n; k++) pe.peer[k] = c->peer.peer[k];
+        if (pe.rank > 0) {  // the lower neighbour's TOP ghost plane = its last stored plane
+            int kn0 = 0, kn1 = 0;
+            TOB_CHECK(tob_slab_partition(g.nzn, pe.n, pe.rank - 1, &kn0, &kn1, nullptr, nullptr));
+            const int gn0 = kn0 > 0 ? kn0 - 1 : 0, gn1 = kn1 + 1;
+            pe.u_lo_ghost = h->sr_u.peer[pe.rank - 1] + (long long)(gn1 - gn0 - 1) * g.pstride;
+        }
+        if (pe.rank < pe.n - 1) pe.u_hi_ghost = h->sr_u.peer[pe.rank + 1];  // its plane 0 is its bottom ghost plane
+        // nobody may store into a peer's buffer before that peer has zeroed it
+        double* d_dummy = c->d_scalars + kScalarSlots - 1;
+        TOB_NCCL(ncclAllReduce(d_dummy, d_dummy, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    }
+    TOB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static void sr_destroy(tob_elast_impl* h) {
+    if (!h->sr_cg) return;
+    if (h->sr_graph) { cudaGraphExecDestroy(h->sr_graph); h->sr_graph = nullptr; }
+    peer_vec_free(h->c, &h->sr_u);
+    cudaFree(h->sr_cg); h->sr_cg = nullptr;
+    cudaFree(h->sr_upart); h->sr_upart = nullptr;
+}
+
+// R holds b - A U on entry; iterates until ||r|| <= tol.  *it / *rnorm as in elast_pcg.
+static int elast_pcg_sr(tob_elast_impl* h, double tol, double bnorm, int* it_out, double* rnorm_out) {
+    tob_ctx_impl* c = h->c;
+    const LevelGrid& g = *h->g;
+    const tob_solver_opts& o = h->opts;
+    TOB_CHECK(sr_setup(h));
+    double* u = h->sr_u.mine;
+    CgState st0{1.0, 1.0, 1.0, c->cg_epoch};
+    TOB_CUDA(cudaMemcpyAsync(&h->sr_cg->st[0], &st0, sizeof st0, cudaMemcpyHostToDevice, c->stream));
+    TOB_CHECK(vec_zero(c, h->P, g.nvec));
+    TOB_CHECK(vec_zero(c, h->Z, g.nvec));
+    int np = 0;
+    // set-up pair: u = D^-1 r (+ halo), w = A u, sums
+    TOB_CHECK(cg_update(c, g, h->sr_cg, 0, 0, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV, h->sr_upart, &h->sr_nbU, h->sr_pe));
+    c->cg_epoch++;
+    h->sr_par = 1;
+    TOB_CHECK(elast_apply(h, u, h->Q, EPI_CGDOT, false, 0, nullptr, &np));
+    int par = 1, it = 0;
+    auto one_iteration = [&]() -> int {
+        TOB_CHECK(cg_update(c, g, h->sr_cg, par, 1, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV, h->sr_upart, &h->sr_nbU, h->sr_pe));
+        c->cg_epoch++;
+        par ^= 1;
+        h->sr_par = par;
+        TOB_CHECK(elast_apply(h, u, h->Q, EPI_CGDOT, false, 0, nullptr, &np));
+        return 0;
+    };
+    const int check = o.check_every > 0 ? o.check_every : 10;
+    const int blk = std::max(2, check & ~1);
+    const bool graphed = !getenv("TOB_PCG_NOGRAPH") && check >= 4;
+    const int stride_saved = h->prof_stride;
+    if (graphed) h->prof_stride = 1;  // the two eager iterations of every round are the timed sample
+    double rnorm = *rnorm_out;
+    double* hs = c->h_scalars + 40;
+    while (it < o.maxits) {
+        TOB_CHECK(one_iteration());
+        TOB_CHECK(one_iteration());
+        it += 2;
+        if (graphed) {
+            if (!h->sr_graph || h->sr_graph_its != blk) {
+                if (h->sr_graph) { cudaGraphExecDestroy(h->sr_graph); h->sr_graph = nullptr; }
+                const bool prof = h->profile;
+                h->profile = false;
+                const long long l0 = c->launches;
+                const unsigned long long e0 = c->cg_epoch;
+                TOB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = 0;
+                for (int k = 0; k < blk && !rc; k++) rc = one_iteration();
+                cudaGraph_t graph = nullptr;
+                cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+                h->profile = prof;
+                c->cg_epoch = e0;  // nothing ran during the capture
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (e != cudaSuccess) TOB_FAIL(std::string("PCG graph capture failed: ") + cudaGetErrorString(e));
+                TOB_CUDA(cudaGraphInstantiate(&h->sr_graph, graph, 0));
+                cudaGraphDestroy(graph);
+                h->sr_graph_its = blk;
+                h->sr_graph_launches = c->launches - l0;
+                c->launches = l0;
+            }
+            TOB_CUDA(cudaGraphLaunch(h->sr_graph, c->stream));
+            c->launches += h->sr_graph_launches;
+            c->cg_epoch += blk;
+            h->stats.spmv_calls += blk;
+            it += blk;
+        }
+        // ||r||^2 as the last U saw it (the residual before its own update: one iteration behind, on the safe side)
+        TOB_CUDA(cudaMemcpyAsync(hs, h->sr_cg->out, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        TOB_CUDA(cudaStreamSynchronize(c->stream));
+        rnorm = sqrt(hs[1]);
+        if (!(rnorm == rnorm)) TOB_FAIL("PCG produced NaN (bad density field)");
+        if (rnorm <= tol || rnorm > o.dtol * bnorm) break;
+    }
+    h->prof_stride = stride_saved;
+    *it_out = it;
+    *rnorm_out = rnorm;
+    return 0;
+}
+
 // PCG on A U = B, warm-started from the resident U (KSPSetInitialGuessNonzero, LinearElasticity.cc:647)
 int elast_pcg(tob_elast_impl* h) {
     tob_ctx_impl* c = h->c;
@@ -107,7 +228,15 @@ int elast_pcg(tob_elast_impl* h) {
     double rnorm = sqrt(rr);
     int it = 0;
     const bool fused = jac && c->desc.nranks == 1 && !getenv("TOB_PCG_UNFUSED");
-    if (rnorm > tol && bnorm > 0 && fused) {
+    // Single-reduction variant: the default on several ranks (latency: 2 launches / 2 NVLink hops per iteration instead of
+    // 6 / 3).  Its recurrences drift from the true residual below ~1e-9, so tight solves keep the classical iteration.
+    // TOB_PCG_SR = 0 / 1 forces it off / on (1 also on one rank).
+    const char* sr_env = getenv("TOB_PCG_SR");
+    const bool sr_ok = jac && (o.spmv_kernel == 0 || o.spmv_kernel == SPMV_ZM16U4) && (c->desc.nranks == 1 || c->peer.enabled);
+    const bool sr = sr_ok && (sr_env ? atoi(sr_env) != 0 : (c->desc.nranks > 1 && o.rtol >= 1e-8));
+    if (rnorm > tol && bnorm > 0 && sr) {
+        TOB_CHECK(elast_pcg_sr(h, tol, bnorm, &it, &rnorm));
+    } else if (rnorm > tol && bnorm > 0 && fused) {
         // single-GPU Jacobi-PCG, 3 launches per iteration: the consumers reduce the producers' per-CTA partials
         // themselves (vecops.cu), no finalize kernels, alpha/beta never leave the device
         double* blk_cur = c->d_partials + (256 << 10);
@@ -403,6 +532,7 @@ void elast_destroy(tob_elast_impl* h) {
     for (auto v : vecs) cudaFree(v);
     for (auto e : h->prof_ev) cudaEventDestroy(e);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
+    sr_destroy(h);
     cudaFree(h->mask);
     hex8_free_operator(h->op);
     delete h;
@@ -444,6 +574,7 @@ int tob_elast_set_opts(tob_elast* hh, const tob_solver_opts* o) {
     const bool need_mg = o->pc == 1 && !h->mg;
     if (h->mg) gmg_drop_graph(h);
     if (h->pcg_graph) { cudaGraphExecDestroy(h->pcg_graph); h->pcg_graph = nullptr; }
+    if (h->sr_graph) { cudaGraphExecDestroy(h->sr_graph); h->sr_graph = nullptr; }
     h->opts = *o;
     if (need_mg) {
         TOB_CHECK(gmg_setup(h));

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "hex8.cuh"
+#include "cgsr.cuh"
 
 namespace tob {
 
@@ -35,6 +36,15 @@ struct tob_elast_impl {
     long long pcg_graph_launches = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
+    // single-reduction Jacobi-PCG (cgsr.cuh): u = D^-1 r lives in a peer-mapped buffer (the neighbours store its ghost planes)
+    PeerVec sr_u;
+    CgDev* sr_cg = nullptr;
+    double* sr_upart = nullptr;
+    CgPeers sr_pe;
+    int sr_nbU = 0, sr_par = 0;
+    cudaGraphExec_t sr_graph = nullptr;
+    int sr_graph_its = 0;
+    long long sr_graph_launches = 0;
 };
 int elast_profile_collect(tob_elast_impl* h);
 

@@ -164,10 +164,10 @@ static int cone_apply_tiled(tob_filter_impl* h, const double* in_st, double* out
     P.hs = h->hs_st; P.xnat = xnat; P.wtab = h->wtab; P.out = out;
     P.nex = g.nex; P.ney = g.ney; P.pe = g.pe; P.l0 = h->own0; P.l1 = h->own1; P.mode = mode; P.estride = h->estride;
     auto kern = k_cone_tiled<S>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // the opt-in is per device
+    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
         TOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
-        attr_set = true;
+        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
     }
     dim3 grid(div_up(g.nex, CT_X), div_up(g.ney, CT_Y), div_up(h->own1 - h->own0, CT_Z));
     kern<<<grid, dim3(CT_X, CT_Y), T::SMEM, c->stream>>>(tm, P);
@@ -272,6 +272,17 @@ int filter_create(tob_ctx_impl* c, int type, double rmin, tob_filter_impl** out)
         s = std::min(s, std::min((g.nxn - 1) / 2, std::min((g.nyn - 1) / 2, (g.nzn - 1) / 2)));
         if (s < 0) s = 0;
         h->s = s;
+        // The ghost layers come from the adjacent rank only, so every rank's slab must be at least s layers thick.  The
+        // partition is known analytically on every rank: all ranks take the same decision, none is left waiting in a recv.
+        for (int r = 0; r < c->desc.nranks && c->desc.nranks > 1; r++) {
+            int e0 = 0, e1 = 0;
+            TOB_CHECK(tob_slab_partition(g.nzn, c->desc.nranks, r, nullptr, nullptr, &e0, &e1));
+            if (e1 - e0 < s) {
+                delete h;
+                TOB_FAIL("cone filter: the ghost width (ElemConn = " + std::to_string(s) + ") exceeds the slab thickness of rank " +
+                         std::to_string(r) + " (" + std::to_string(e1 - e0) + " element layers); use fewer ranks or a smaller rmin");
+            }
+        }
         h->tiled = !(getenv("TOB_CONE_TILED") && atoi(getenv("TOB_CONE_TILED")) == 0);  // 0: direct-gather kernel (A/B, cross-check)
         const int lo = std::min(s, g.ke0), hi = std::min(s, g.nez - g.ke1);
         h->gl0 = g.ke0 - lo;

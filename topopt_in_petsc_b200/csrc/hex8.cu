@@ -16,6 +16,7 @@
 #include "hex8.cuh"
 #include "tma.cuh"
 #include "vecops.cuh"
+#include "cgsr.cuh"
 
 namespace tob {
 
@@ -106,6 +107,14 @@ int hex8_build_operator(double dx, double dy, double dz, double nu, Hex8Operator
             op.blocks.b[1 << c][3 * c + c2] = 0.0;
             op.blocks.b[1 << c][3 * c2 + c] = 0.0;
         }
+    // mixed blocks: entry (c,d), c != d, vanishes unless bits c and d of rho agree (the gen-2 kernel skips those products)
+    for (int rho = 0; rho < 8; rho++)
+        for (int c = 0; c < 3; c++)
+            for (int c2 = 0; c2 < 3; c2++)
+                if (c != c2 && (((rho >> c) & 1) != ((rho >> c2) & 1))) {
+                    if (fabs(op.blocks.b[rho][3 * c + c2]) > 1e-12 * dmax) TOB_FAIL("symmetry block has an unexpected coupling");
+                    op.blocks.b[rho][3 * c + c2] = 0.0;
+                }
     for (int c = 0; c < 3; c++) op.kdiag[c] = op.KE[c * 24 + c];
     for (int n = 1; n < 8; n++)
         for (int c = 0; c < 3; c++)
@@ -181,6 +190,13 @@ struct ZmParams {
     double s0, s1;
     double* partials;
     int l2hint;  // Jacobi-PCG only (common.cuh): 1 = modulus tiles evict_first, 2 = input vector (p) evict_last
+    // EPI_CGDOT (single-reduction PCG, cgsr.cuh): wait for the neighbours' ghost planes, last CTA reduces and publishes
+    CgDev* cg;
+    int cgpar;            // parity of the state the preceding U kernel wrote (holds the epoch of this operand)
+    const double* upart;  // U's per-CTA partials: [0,nbU) r.u, [nbU,2nbU) r.r
+    int nbU;
+    CgPeers pe;
+    size_t red_off0, red_off1;
 };
 
 // TMA tiles are ZM_W = 34 doubles wide: with a non-swizzled tensor map the innermost start
@@ -491,6 +507,15 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
     }
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // z-march, generation 2: the mbarrier hand-off kernel above with the march unrolled by STAGES (= 4).
 // What the unrolling buys (SASS of the gen-1 loop: 366 instructions per warp-step for 177 DP -- issue slots, not the
@@ -538,11 +563,26 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int pfirst = z0 - 1;
     const int nplanes = z1 - z0 + 2;
     double part = 0.0;
+    // Rows whose node row lies outside the grid (j = -1 in the first tile row, j >= nyn in the last) have nothing to
+    // compute and nothing to write: they stay out of the march altogether (fewer warps on the FP64 pipe in the edge tiles).
+    const int ja = max(j0, 0), jb = min(j0 + NCOMP - 1, P.nyn - 1);  // active element rows: node rows ja..jb
+    const int nactive = jb - ja + 1;
+    const bool rowactive = (j >= ja) && (j <= jb) && (ty < NCOMP);
 
     if (z0 < z1) {
         if (tid == 0) {
+            if (EPI == EPI_CGDOT && P.pe.n > 1) {
+                // the boundary planes of the operand are stored into my ghost planes by the neighbours' U kernels: only the
+                // chunks that read a ghost plane wait (system-scope acquire of the epoch flag in my arena)
+                const unsigned long long e = P.cg->st[P.cgpar].epoch;
+                const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(P.pe.arena);
+                if (z0 == P.zout0 && P.pe.rank > 0)
+                    while (ld_acquire_sys_u64(&flags[F_CG_FROM_LO]) < e) {}
+                if (z1 == P.zout1 && P.pe.rank < P.pe.n - 1)
+                    while (ld_acquire_sys_u64(&flags[F_CG_FROM_HI]) < e) {}
+            }
             for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
-            for (int s = 0; s < L::STAGES; s++) mbar_init(&ebars[s], NCOMP);
+            for (int s = 0; s < L::STAGES; s++) mbar_init(&ebars[s], nactive);
             for (int s = 0; s < TY * L::XCH_DEPTH; s++) mbar_init(&xbars[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -559,14 +599,14 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             if (P.l2hint & 1) tma_load_3d_hint(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1, l2_policy_first());
             else tma_load_3d(st + L::U_BYTES, &tmE, &bars[s], i0 - 1, j0, p - 1);
         };
-        const bool refills = MERGED && ty == TY - 1;
+        const bool refills = MERGED && j == jb;  // the last ACTIVE row
         if (!MERGED && ty == TY - 1) {
             // ---- dedicated producer row ----------------------------------------------------------
             for (int q = 0; q < nplanes; q++) {
                 if (q >= L::STAGES) mbar_wait(&ebars[q & 3], ((q >> 2) - 1) & 1);
                 if (tx == 0) issue(q);
             }
-        } else {
+        } else if (rowactive) {
             if (refills && tx == 0)
                 for (int q = 0; q < L::STAGES && q < nplanes; q++) issue(q);
             // ---- consumer rows ---------------------------------------------------------------
@@ -580,7 +620,7 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             double* xw0 = xch + o2;
             uint64_t* xb_mine = &xbars[ty * 4];
             uint64_t* xb_below = &xbars[(ty - 1) * 4];
-            const bool has_below = ty >= 1, signals = ty < NCOMP - 1;
+            const bool has_below = j > ja, signals = j < jb;
 
             auto face_modes = [&](const double* su, double (&fm)[12], double (&own)[3]) {
 #pragma unroll
@@ -640,32 +680,33 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                             uh[c][4 + f] = fl[4 * c + f] - fn[4 * c + f];
                         }
                     double yh[3][8];
+                    // Block rho couples (mode rho^(1<<c), component c), c = 0..2.  Entry (c,d), c != d, is non-zero only when
+                    // bits c and d of rho are equal (both derivatives come from the lambda term or both from the mu term);
+                    // (c,c) vanishes for rho == 1<<c (rigid translation).  So rho = 0,7 are full symmetric 3x3, rho = 1,2,4 a
+                    // 2x2, rho = 3,5,6 a 2x2 plus a 1x1: 45 DP operations instead of 72 (checked in hex8_build_operator).
 #pragma unroll
                     for (int rho = 0; rho < 8; rho++) {
-                        const double in0 = uh[0][rho ^ 1], in1 = uh[1][rho ^ 2], in2 = uh[2][rho ^ 4];
+                        const double in[3] = {uh[0][rho ^ 1], uh[1][rho ^ 2], uh[2][rho ^ 4]};
                         const double2 k0 = kz[rho * 3 + 0], k1 = kz[rho * 3 + 1], k2 = kz[rho * 3 + 2];
-                        const double b00 = k0.x, b01 = k0.y, b02 = k1.x, b11 = k1.y, b12 = k2.x, b22 = k2.y;
-                        double o0, o1, o2v;
-                        if (rho == 1) {
-                            o0 = 0.0;
-                            o1 = b11 * in1 + b12 * in2;
-                            o2v = b12 * in1 + b22 * in2;
-                        } else if (rho == 2) {
-                            o1 = 0.0;
-                            o0 = b00 * in0 + b02 * in2;
-                            o2v = b02 * in0 + b22 * in2;
-                        } else if (rho == 4) {
-                            o2v = 0.0;
-                            o0 = b00 * in0 + b01 * in1;
-                            o1 = b01 * in0 + b11 * in1;
-                        } else {
-                            o0 = b00 * in0 + b01 * in1 + b02 * in2;
-                            o1 = b01 * in0 + b11 * in1 + b12 * in2;
-                            o2v = b02 * in0 + b12 * in1 + b22 * in2;
+                        const double b[3][3] = {{k0.x, k0.y, k1.x}, {k0.y, k1.y, k2.x}, {k1.x, k2.x, k2.y}};
+                        double o3[3];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            double acc = 0.0;
+                            bool first = true;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                const bool active = (c == d) ? (rho != (1 << c)) : (((rho >> c) & 1) == ((rho >> d) & 1));
+                                if (active) {
+                                    acc = first ? b[c][d] * in[d] : fma(b[c][d], in[d], acc);
+                                    first = false;
+                                }
+                            }
+                            o3[c] = acc;
                         }
-                        yh[0][rho ^ 1] = o0;
-                        yh[1][rho ^ 2] = o1;
-                        yh[2][rho ^ 4] = o2v;
+                        yh[0][rho ^ 1] = o3[0];
+                        yh[1][rho ^ 2] = o3[1];
+                        yh[2][rho ^ 4] = o3[2];
                     }
                     double ht[3][4];
 #pragma unroll
@@ -711,7 +752,7 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                         const double au = fixed ? uo[c] : v[c];
                         if (EPI == EPI_Y) {
                             yp[c * P.nstride] = au;
-                        } else if (EPI == EPI_DOT) {
+                        } else if (EPI == EPI_DOT || EPI == EPI_CGDOT) {
                             yp[c * P.nstride] = au;
                             part = fma(uo[c], au, part);
                         } else if (EPI == EPI_RESID) {
@@ -751,9 +792,44 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             }
         }
     }
-    if (EPI == EPI_DOT || EPI == EPI_RESID) {
+    if (EPI == EPI_DOT || EPI == EPI_RESID || EPI == EPI_CGDOT) {
         part = block_sum(part, red);
         if (tid == 0) P.partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = part;
+    }
+    if (EPI == EPI_CGDOT) {
+        // the last CTA to finish reduces every partial of this iteration (U's r.u and r.r, this kernel's w.u) in a fixed
+        // order and publishes the three sums: locally on one rank, into every peer's arena (+ epoch flag) otherwise
+        __shared__ int s_last;
+        const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
+        if (tid == 0) {
+            __threadfence();
+            s_last = (atomicAdd(&P.cg->scounter, 1u) == nblk - 1u);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double a = 0.0, b = 0.0, d = 0.0;
+            for (int k = tid; k < P.nbU; k += blockDim.x) { a += __ldcg(P.upart + k); b += __ldcg(P.upart + P.nbU + k); }
+            for (unsigned int k = tid; k < nblk; k += blockDim.x) d += __ldcg(P.partials + k);
+            a = block_sum(a, red);
+            b = block_sum(b, red);
+            d = block_sum(d, red);
+            __shared__ double s_sum[3];
+            if (tid == 0) { s_sum[0] = a; s_sum[1] = b; s_sum[2] = d; P.cg->scounter = 0u; }
+            __syncthreads();
+            if (P.pe.n == 1) {
+                if (tid < 3) P.cg->sums[tid] = s_sum[tid];
+            } else {
+                const unsigned long long e = P.cg->st[P.cgpar].epoch;
+                const size_t off = ((e & 1) ? P.red_off1 : P.red_off0) + (size_t)P.pe.rank * 128 * 8;
+                if (tid < P.pe.n) {
+                    double* dst = reinterpret_cast<double*>(P.pe.peer[tid] + off) + kCgSlot;
+                    dst[0] = s_sum[0]; dst[1] = s_sum[1]; dst[2] = s_sum[2];
+                    __threadfence_system();
+                    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.pe.peer[tid]) + F_CG_RED0 + P.pe.rank, e);
+                }
+            }
+        }
     }
 }
 
@@ -782,6 +858,10 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1();
     P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
     P.l2hint = a.l2hint;
+    P.cg = a.cg; P.cgpar = a.cgpar; P.upart = a.upart; P.nbU = a.nbU;
+    if (a.pe) P.pe = *a.pe; else P.pe = CgPeers();
+    P.red_off0 = P.pe.n > 1 ? cg_red_off(P.pe.n, 0, 0) : 0;
+    P.red_off1 = P.pe.n > 1 ? cg_red_off(P.pe.n, 1, 0) : 0;
     const int gx = div_up(g.nxn, 30), gy = div_up(g.nyn, ROWS - 2);
     const int nz = P.zout1 - P.zout0;
     // z-chunks: every chunk recomputes one element layer and pays a prologue, and the grid runs in waves
@@ -824,7 +904,7 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, kp, P);
     c->launches++;
     TOB_KERNEL_CHECK();
-    if (nparts) *nparts = (EPI == EPI_DOT || EPI == EPI_RESID) ? gx * gy * nch : 0;
+    if (nparts) *nparts = (EPI == EPI_DOT || EPI == EPI_RESID || EPI == EPI_CGDOT) ? gx * gy * nch : 0;
     return 0;
 }
 
@@ -834,6 +914,9 @@ static int dispatch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& 
         case EPI_Y: return launch_zm<TY, EPI_Y, FLAGS, GEN>(c, g, op, a, nparts);
         case EPI_DOT: return launch_zm<TY, EPI_DOT, FLAGS, GEN>(c, g, op, a, nparts);
         case EPI_RESID: return launch_zm<TY, EPI_RESID, FLAGS, GEN>(c, g, op, a, nparts);
+        case EPI_CGDOT:
+            if constexpr (GEN == 2 && TY == 16) return launch_zm<TY, EPI_CGDOT, FLAGS, GEN>(c, g, op, a, nparts);
+            else TOB_FAIL("the single-reduction PCG epilogue exists for the default SpMV kernel only");
         default: return launch_zm<TY, EPI_CHEB, FLAGS, GEN>(c, g, op, a, nparts);
     }
 }
@@ -842,7 +925,7 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
     if (nparts) *nparts = 0;
     // measured (profiles/r01_spmv_probe_v6.txt): the mbarrier hand-off kernel with 32x16 tiles wins at every size tried
     // (192x96x96: 43 us vs 49 (same tile, __syncthreads) / 57-61 (32x8 tiles); 256^3: 0.325 ms vs 0.385 / 0.362-0.391)
-    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM16RF : a.kernel;
+    int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM16U4 : a.kernel;  // gen 2 (profiles/r02_spmv_probe_*.txt)
     if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
     if (kernel == SPMV_NAIVE) {
         if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");

@@ -25,7 +25,9 @@ void hex8_element_matrix(double dx, double dy, double dz, double nu, double* ke5
 int hex8_build_operator(double dx, double dy, double dz, double nu, Hex8Operator& op);
 void hex8_free_operator(Hex8Operator& op);
 
-enum SpmvEpilogue { EPI_Y = 0, EPI_DOT = 1, EPI_RESID = 2, EPI_CHEB = 3 };
+enum SpmvEpilogue { EPI_Y = 0, EPI_DOT = 1, EPI_RESID = 2, EPI_CHEB = 3, EPI_CGDOT = 4 };
+struct CgDev;
+struct CgPeers;
 enum SpmvKernel { SPMV_AUTO = 0, SPMV_NAIVE = 1, SPMV_ZM8 = 2, SPMV_ZM16 = 3, SPMV_ZM12 = 4, SPMV_ZM8R = 5, SPMV_ZM8RF = 6, SPMV_ZM16RF = 7, SPMV_ZM12RF = 8, SPMV_ZM16R = 9, SPMV_ZM16U4 = 10, SPMV_ZM16M4 = 11 };
 
 struct SpmvArgs {
@@ -42,6 +44,12 @@ struct SpmvArgs {
     double* o1 = nullptr;                // CHEB: d (in/out)
     double s0 = 0, s1 = 0;               // CHEB: d = s0*d + s1*dinv*(b - A u); y = u + d
     int l2hint = 0;                      // L2 eviction hints for the TMA loads (Jacobi-PCG; tob_ctx_impl::l2hint)
+    // EPI_CGDOT (cgsr.cuh): y = A u, partials of u.y, last CTA reduces U's and its own partials and publishes the sums
+    CgDev* cg = nullptr;
+    int cgpar = 0;
+    const double* upart = nullptr;
+    int nbU = 0;
+    const CgPeers* pe = nullptr;
 };
 
 // y = N.(K (N.u)) + (1-N).u on the owned planes of level grid g; *nparts = number of per-CTA partial
