@@ -165,6 +165,13 @@ int tob_mma_design_change(tob_mma* h, const double* x, double* xold, double* ch)
 int tob_mma_get_restart(tob_mma* h, double* xo1, double* xo2, double* U, double* L, int* k);
 int tob_mma_set_restart(tob_mma* h, const double* xo1, const double* xo2, const double* U, const double* L, int k);
 
+/* ---- diagnostics for the parity tests -------------------------------------------------------------------------------- */
+/* Levels of the multigrid hierarchy (replaces PCMGSetLevels, LinearElasticity.cc:691) and, for a Galerkin level (the R A P
+ * product of PCMGSetGalerkin, :702), its assembled 27-point block stencil A[243][nz*ny*px], k = 9*offset + 3*c + c2;
+ * dims = {nx, ny, nz, px}.  out may be NULL to query dims / is_stencil only. */
+int tob_elast_gmg_nlevels(tob_elast* h, int* nlevels);
+int tob_elast_gmg_level_stencil(tob_elast* h, int level, double* out, int* dims, int* is_stencil);
+
 /* ---- micro-benchmarks used to size the kernels (profiles/) ------------ */
 /* kind 0: DFMA stream, 1: DMMA m8n8k4 stream, 2: both interleaved; returns TFLOP/s (fp64) */
 int tob_microbench_fp64(tob_ctx* ctx, int kind, double* tflops);

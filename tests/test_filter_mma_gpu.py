@@ -184,3 +184,30 @@ def test_pde_filter_vs_oracle(oracle, shape, xc, rmin):
     assert np.abs(df - df0).max() <= 1e-6 * np.abs(df0).max() + 1e-9
     assert np.abs(dg - dg0[0]).max() <= 1e-6 * np.abs(dg0[0]).max() + 1e-12
     f.close(); ctx.close()
+
+
+def test_pde_filter_multigrid_large_radius(oracle, monkeypatch):
+    """rmin = 8 cells on 64x32x32: the V-cycle-preconditioned CG (reference: FGMRES + 3-level PCMG, PDEFilter.cc:276-295,
+    327-378) needs a handful of iterations where Jacobi-PCG needs many; both reproduce the oracle's sparse solve."""
+    from topopt_in_petsc_b200 import Context, Filter
+    rng = np.random.default_rng(4)
+    shape = (65, 33, 33)
+    g = oracle.Grid(*shape)
+    rmin = 8 * g.dx
+    x = rng.uniform(0, 1, g.nel)
+    ref = oracle.PDEFilterOracle(g, rmin).apply(x)
+    ctx = Context(*shape)
+    monkeypatch.setenv("TOB_PDE_MG", "0")
+    fj = Filter(ctx, 2, rmin)
+    oj = fj.PDEApply(x)
+    sj = fj.stats()
+    monkeypatch.setenv("TOB_PDE_MG", "1")
+    fm = Filter(ctx, 2, rmin)
+    om = fm.PDEApply(x)
+    sm = fm.stats()
+    print(f"PDE filter rmin = 8h: Jacobi-PCG {sj.iterations} its {sj.seconds * 1e3:.2f} ms, MG-PCG {sm.iterations} its {sm.seconds * 1e3:.2f} ms")
+    assert sm.rel_residual <= 1e-8 and sj.rel_residual <= 1e-8
+    assert np.abs(om - ref).max() <= 1e-8 and np.abs(oj - ref).max() <= 1e-8
+    assert sm.iterations <= 15 and sm.iterations * 3 < sj.iterations
+    assert np.abs(fm.PDEApply(np.full(g.nel, 0.4)) - 0.4).max() <= 1e-8
+    fj.close(); fm.close(); ctx.close()

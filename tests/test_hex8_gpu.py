@@ -378,3 +378,45 @@ def test_single_reduction_pcg_on_one_rank(oracle, dens, monkeypatch):
     s2 = sr.SolveState(0.9 * x + 0.05, 1e-9, 1.0, 3.0)  # warm-started second solve through the captured graph
     assert s2.rel_residual <= 1e-8
     cl.close(); sr.close(); ctx.close()
+
+
+def test_galerkin_coarse_operators_match_ptap(oracle, monkeypatch):
+    """Galerkin levels of the multigrid hierarchy (galerkin.cu; the reference: PCMGSetGalerkin, LinearElasticity.cc:702):
+    with TOB_GMG_GALERKIN_FROM=1 level 1 is assembled from the matrix-free fine level, level 2 from level 1's stencil.
+    Both must equal N (P^T A P) N + (I - N) formed with scipy from the oracle's assembled matrix and Q1 prolongation."""
+    import scipy.sparse as sp
+    from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
+    monkeypatch.setenv("TOB_GMG_GALERKIN_FROM", "1")
+    rng = np.random.default_rng(21)
+    shape = (17, 9, 13)
+    g = oracle.Grid(*shape)
+    x = rng.uniform(0.0, 1.0, g.nel) ** 3
+    KE = oracle.hex8_ke(g.dx, g.dy, g.dz, 0.3)
+    N0, _ = oracle.cantilever_bc_load(g)
+    K0 = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, np.ones(g.ndof))  # unconstrained: the masks enter level by level
+    ctx = Context(*shape)
+    mg = LinearElasticity(ctx, opts=solver_opts(pc=1, nlvls=3, rtol=1e-8, maxits=200))
+    mg.SetDensity(x, 1e-9, 1.0, 3.0)
+    assert mg.GmgLevels() == 3 and mg.GmgLevelMatrix(0) is None
+    A_prev, dims = K0, (17, 9, 13)
+    for lvl in (1, 2):
+        nc = tuple((d - 1) // 2 + 1 for d in dims)
+        P = oracle.q1_prolongation(*nc)
+        gc = oracle.Grid(*nc)
+        Nc, _ = oracle.cantilever_bc_load(gc)  # injection of the wall x = xmin
+        D = sp.diags(Nc)
+        ref = (D @ (P.T @ A_prev @ P) @ D + sp.diags(1.0 - Nc)).tocsr()
+        got = mg.GmgLevelMatrix(lvl)
+        assert got is not None
+        assert abs(got - ref).max() <= 1e-12 * abs(ref).max(), (lvl, abs(got - ref).max() / abs(ref).max())
+        # the next level is the product of THIS level's operator without its Dirichlet rows: rebuild the unconstrained one
+        A_prev, dims = (P.T @ A_prev @ P).tocsr(), nc
+    # and the preconditioned solve converges to the direct solution
+    import scipy.sparse.linalg as spla
+    _, RHS = oracle.cantilever_bc_load(g)
+    K = oracle.assemble_K(g, KE, x, 1e-9, 1.0, 3.0, N0)
+    U = spla.spsolve(K.tocsc(), N0 * RHS)
+    st = mg.SolveState(x, 1e-9, 1.0, 3.0)
+    assert st.rel_residual <= 1e-8 and st.iterations < 60, st.iterations
+    assert np.abs(mg.GetStateField() - U).max() <= 1e-5 * np.abs(U).max()
+    mg.close(); ctx.close()

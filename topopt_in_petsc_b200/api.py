@@ -210,6 +210,36 @@ class LinearElasticity:
         check(self.lib.tob_elast_get_rhs(self.h, r.ctypes.data))
         return r
 
+    def GmgLevels(self):
+        n = C.c_int()
+        check(self.lib.tob_elast_gmg_nlevels(self.h, C.byref(n)))
+        return n.value
+
+    def GmgLevelMatrix(self, level):
+        """None for a matrix-free level; for a Galerkin level the assembled operator as scipy CSR in the oracle's dof order
+        (3 * node + c, node = i + nx * (j + ny * k))."""
+        import scipy.sparse as sp
+        dims, st = (C.c_int * 4)(), C.c_int()
+        check(self.lib.tob_elast_gmg_level_stencil(self.h, level, None, dims, C.byref(st)))
+        if not st.value:
+            return None
+        nx, ny, nz, px = list(dims)
+        A = np.empty((243, nz, ny, px))
+        check(self.lib.tob_elast_gmg_level_stencil(self.h, level, A.ctypes.data, dims, C.byref(st)))
+        A = A[:, :, :, :nx].reshape(27, 3, 3, nz, ny, nx)
+        k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        rows, cols, vals = [], [], []
+        for o in range(27):
+            di, dj, dk = o % 3 - 1, (o // 3) % 3 - 1, o // 9 - 1
+            ok = (i + di >= 0) & (i + di < nx) & (j + dj >= 0) & (j + dj < ny) & (k + dk >= 0) & (k + dk < nz)
+            n = (i + nx * (j + ny * k))[ok]
+            m = ((i + di) + nx * ((j + dj) + ny * (k + dk)))[ok]
+            for c in range(3):
+                for c2 in range(3):
+                    rows.append(3 * n + c); cols.append(3 * m + c2); vals.append(A[o, c, c2][ok])
+        nd = 3 * nx * ny * nz
+        return sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nd, nd)).tocsr()
+
     def SetProfile(self, on=True):
         check(self.lib.tob_elast_set_profile(self.h, int(on)))
 

@@ -18,6 +18,7 @@
 //     whole coarse grid -- no halo, no all-reduce, and as many levels as the global grid allows.  Coarse levels are
 //     launch-latency bound, so redundant work costs nothing while every exchange on them costs a latency.
 #include "elast.cuh"
+#include "galerkin.cuh"
 #include "vecops.cuh"
 
 namespace tob {
@@ -30,6 +31,8 @@ struct GmgLevel {
     unsigned char* mask = nullptr;
     bool own_E = false;
     int res = 0;  // resolution index: this level's elements are 2^res fine elements wide
+    bool stencil = false;  // Galerkin level: the operator is the assembled block stencil S (galerkin.cu)
+    StencilLevel S;
 };
 
 struct GmgHierarchy {
@@ -170,7 +173,8 @@ static double element_rayleigh_bound(const double* KE) {
     return lam;
 }
 
-static int level_apply(tob_elast_impl* h, GmgLevel& L, const SpmvArgs& a0, int* nparts) {
+static int level_apply(tob_elast_impl* h, GmgLevel& L, const SpmvArgs& a0, int* nparts, int step = 0) {
+    if (L.stencil) return stencil_apply(h->c, L.S, L.g, a0.epi, a0.u, a0.y, a0.a0, a0.a1, a0.o1, step, nparts);
     SpmvArgs a = a0;
     a.E = L.E; a.mask = L.mask; a.mask_in = false;
     a.kernel = h->opts.spmv_kernel;
@@ -199,6 +203,7 @@ static int cheb_smooth(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
         }
         if (s == 0 && zero_init) {
             const LevelGrid& g = L.g;
+            if (L.stencil) { TOB_CHECK(stencil_cheb_first(c, L.S, g, xin, L.d, L.b, L.dinv)); continue; }
             k_cheb_first<<<flat_grid(c, g.own_len), kFlatThreads, 0, c->stream>>>(xin + g.own_off, L.d + g.own_off, L.b + g.own_off,
                                                                                 L.dinv + g.own_off, s1, g.own_len);
             c->launches++;
@@ -208,7 +213,7 @@ static int cheb_smooth(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
         TOB_CHECK(halo_nodes(c, L.g, xin));
         SpmvArgs a;
         a.u = xin; a.y = xout; a.epi = EPI_CHEB; a.a0 = L.b; a.a1 = L.dinv; a.o1 = L.d; a.s0 = s0; a.s1 = s1;
-        TOB_CHECK(level_apply(h, L, a, nullptr));
+        TOB_CHECK(level_apply(h, L, a, nullptr, s));  // Galerkin levels read their coefficients from the device (step s)
         double* t = xin; xin = xout; xout = t;
     }
     // keep the buffer roles fixed (the V-cycle is replayed as a CUDA graph): copy back instead of swapping pointers
@@ -221,6 +226,8 @@ static int coarse_solve(tob_elast_impl* h, GmgLevel& L, int its) {
     tob_ctx_impl* c = h->c;
     GmgHierarchy* mg = h->mg;
     const LevelGrid& g = L.g;
+    if (L.stencil)  // Jacobi-PCG to a relative residual inside one CTA: no launches, no host, (almost) exact -> linear preconditioner
+        return stencil_coarse_solve(c, L.S, g, L.dinv, L.b, L.x, L.r, mg->cp, mg->cq, 1.0e-6, 40 * its);
     TOB_CHECK(vec_zero(c, L.x, g.nvec));
     TOB_CHECK(vec_copy(c, L.r, L.b, g.nvec));
     int cur = G_S_PAIR_A, nxt = G_S_PAIR_B, np = 0;
@@ -347,6 +354,12 @@ int gmg_update(tob_elast_impl* h) {
             TOB_CHECK(hex8_diag_inv(c, g, C.op, C.E, C.mask, C.dinv, true));
             continue;
         }
+        if (C.stencil) {  // Galerkin product P^T A P (LinearElasticity.cc:702), redone with every new design (:198-200)
+            if (F.stencil) TOB_CHECK(stencil_assemble_from_stencil(c, f, F.S, g, C.mask, C.S));
+            else TOB_CHECK(stencil_assemble_from_mf(c, f, F.E, F.op.KE, g, C.mask, C.S));
+            TOB_CHECK(stencil_finish(c, g, C.S, C.dinv, mg->lam_ratio, std::max(1, h->opts.cheb_degree), 8));
+            continue;
+        }
         const int nlc = g.ke1 - g.ke0;
         dim3 grid(div_up(g.nex, 128), g.ney, nlc);
         k_coarsen_E<<<grid, 128, 0, c->stream>>>(F.E, C.E, g.nex, g.ney, f.pe, g.pe, f.estride, g.estride, f.ke0 - f.ge0,
@@ -426,7 +439,18 @@ int gmg_setup(tob_elast_impl* h) {
         }
         double** vs[] = {&L.x, &L.x2, &L.b, &L.r, &L.d};
         for (auto v : vs) TOB_CHECK(galloc(c, v, L.g.nvec));
+        // Galerkin levels: from resolution index gf down, where the level is small (whole grid on this rank) -- the first two
+        // coarsenings stay re-discretised: with the density filter a member is several elements wide, so the 8-child mean is
+        // still a faithful operator there, and an assembled level 1 would cost 4x the traffic of the matrix-free fine level
+        const int gf = getenv("TOB_GMG_GALERKIN_FROM") ? atoi(getenv("TOB_GMG_GALERKIN_FROM")) : 2;
+        const bool whole = (nranks == 1) || L.g.replicated;
+        if (l > 0 && gf > 0 && L.res >= gf && whole && !(dI >= 0 && l == dI + 1) && (long long)L.g.nxn * L.g.nyn * L.g.nzn <= 2000000) {
+            L.stencil = true;
+            TOB_CHECK(stencil_alloc(c, L.g, L.S));
+        }
     }
+    for (int l = 1; l < nl; l++)  // a Galerkin level needs every deeper level to be Galerkin too (its children are not re-discretised from E)
+        if (mg->lv[l - 1].stencil && !mg->lv[l].stencil) TOB_FAIL("internal: Galerkin levels must be contiguous down to the coarsest");
     if (dI >= 0) {  // chunks of the gather from lv[dI] (distributed) to lv[dI+1] (replicated, same pitches)
         const LevelGrid& d = mg->lv[dI].g;
         const LevelGrid& t = mg->lv[dI + 1].g;
@@ -484,6 +508,7 @@ void gmg_destroy(tob_elast_impl* h) {
         double* vs[] = {L.x, L.x2, L.b, L.r, L.d};
         for (auto v : vs) cudaFree(v);
         if (L.own_E) { cudaFree(L.E); cudaFree(L.dinv); cudaFree(L.mask); }
+        if (L.stencil) stencil_free(L.S);
         if (L.own_op) hex8_free_operator(L.op);
     }
     cudaFree(mg->cp);
@@ -493,3 +518,24 @@ void gmg_destroy(tob_elast_impl* h) {
 }
 
 }  // namespace tob
+
+// diagnostics for the parity tests: the assembled block stencil of a Galerkin level, A[243][nz*ny*px] -> out; dims = {nx, ny, nz, px}
+extern "C" int tob_elast_gmg_level_stencil(tob_elast* hh, int level, double* out, int* dims, int* is_stencil) {
+    using namespace tob;
+    auto* h = reinterpret_cast<tob_elast_impl*>(hh);
+    if (!h->mg) TOB_FAIL("no multigrid hierarchy (pc = 1 needed)");
+    if (level < 0 || level >= (int)h->mg->lv.size()) TOB_FAIL("no such level");
+    GmgLevel& L = h->mg->lv[level];
+    if (dims) { dims[0] = L.g.nxn; dims[1] = L.g.nyn; dims[2] = L.g.nzn; dims[3] = L.g.px; }
+    if (is_stencil) *is_stencil = L.stencil ? 1 : 0;
+    if (out && L.stencil) {
+        TOB_CUDA(cudaMemcpyAsync(out, L.S.A, sizeof(double) * 243 * L.S.nnp, cudaMemcpyDeviceToHost, h->c->stream));
+        TOB_CUDA(cudaStreamSynchronize(h->c->stream));
+    }
+    return 0;
+}
+extern "C" int tob_elast_gmg_nlevels(tob_elast* hh, int* n) {
+    auto* h = reinterpret_cast<tob::tob_elast_impl*>(hh);
+    *n = h->mg ? (int)h->mg->lv.size() : 0;
+    return 0;
+}

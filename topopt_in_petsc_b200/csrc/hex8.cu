@@ -1009,9 +1009,9 @@ k_hex8_compliance(const double* __restrict__ u, const double* __restrict__ xphys
     __shared__ double red[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
-    const int l = l0 + blockIdx.z;  // local element layer
     double pf = 0.0, px_sum = 0.0;
-    if (i < nex && l < l1) {
+    // grid.z may be smaller than the number of layers (partial-sum buffer): every CTA strides over layers
+    for (int l = l0 + blockIdx.z; i < nex && l < l1; l += gridDim.z) {
         double uh[3][8];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -1038,8 +1038,8 @@ k_hex8_compliance(const double* __restrict__ u, const double* __restrict__ xphys
         }
         const long long eidx = l * estride + (long long)j * pe + i;
         const double xp = xphys[eidx];
-        pf = E[eidx] * uKu;
-        px_sum = xp;
+        pf += E[eidx] * uKu;
+        px_sum += xp;
         dfdx[(long long)i + (long long)nex * (j + (long long)ney * (l - l0))] = -penal * pow(xp, penal - 1.0) * dE * uKu;
     }
     pf = block_sum(pf, red);
@@ -1056,11 +1056,11 @@ int hex8_compliance(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op,
                     const double* E, double penal, double Emin, double Emax, double* dfdx_nat, int slot) {
     const int l0 = g.ke0 - g.ge0, l1 = g.ke1 - g.ge0;
     dim3 grid(div_up(g.nex, 128), g.ney, l1 - l0);
+    // two partial sums per CTA must fit the buffer: on large slabs the CTAs stride over the layers instead
+    const long long per_layer = (long long)grid.x * grid.y;
+    if (2 * per_layer > kMaxPartials) TOB_FAIL("compliance: one element layer exceeds the partial-sum buffer");
+    grid.z = (unsigned)std::max(1LL, std::min<long long>(l1 - l0, kMaxPartials / 2 / per_layer));
     const long long nb = (long long)grid.x * grid.y * grid.z;
-    if (2 * nb > kMaxPartials) {
-        // large grids: fall back to chunks along z so the partial buffer suffices
-        TOB_FAIL("compliance partial buffer too small");
-    }
     k_hex8_compliance<<<grid, 128, 0, c->stream>>>(u, xphys, E, dfdx_nat, op.blocks, g.nex, g.ney, g.px, g.pe, g.nstride,
                                                    g.pstride, g.estride, l0, l1, penal, Emax - Emin, c->d_partials);
     c->launches++;

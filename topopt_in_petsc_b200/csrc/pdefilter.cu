@@ -3,8 +3,13 @@
 //   FilterProject (PDEFilter.cc:189-216):  RHS = T x ; U0 = RHS ; RHS *= elemVol ; solve K U = RHS ; out = T^T U
 // K = sum_e KF is a constant-coefficient 27-point operator (boundary nodes simply have fewer elements),
 // applied matrix-free from the 8 distinct entries of the 8x8 element matrix KF; T[node,elem] = 1/8.
-// K = R^2 * stiffness + mass is well conditioned for filter radii of a few cells, so the solver is
-// Jacobi-preconditioned CG to the reference's tolerance (rtol 1e-8, PDEFilter.cc:279), all scalars on the device.
+// Solver: CG to the reference's tolerance (rtol 1e-8, PDEFilter.cc:279), preconditioned by a geometric-multigrid V-cycle
+// (the reference: FGMRES(20) + 3-level PCMG with GMRES(1)+Jacobi smoothers, PDEFilter.cc:276-295, 327-378): the scalar
+// grid is coarsened by 2 while every dimension and every slab boundary stays even, each level applies the SAME
+// constant-coefficient 27-point kernel with its own element size (re-discretisation is exact here: constant coefficients),
+// smoother = Chebyshev-Jacobi with a Gershgorin bound computed on the host, Q1 transfers, the coarsest level is smoothed
+// harder.  Without a coarsenable grid (or with TOB_PDE_MG=0) it is Jacobi-PCG as in round 1: the iteration count of that
+// one grows like rmin/h and dominated BASELINE configs[3].
 #include "filter.cuh"
 #include "vecops.cuh"
 
@@ -12,7 +17,17 @@ namespace tob {
 
 enum { P_S_PQ = 48, P_S_BB = 49, P_S_PAIR_A = 50, P_S_PAIR_B = 52 };
 
+struct PdeLevel {
+    LevelGrid g;           // scalar nodal grid of this level
+    double kf[8];
+    double lam = 2.0;      // bound on lambda_max(D^-1 K)
+    double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *dinv = nullptr;
+};
+
 struct PdeFilterState {
+    std::vector<PdeLevel> lv;  // lv[0] aliases the fine grid (gs, kf, DINV); empty = no multigrid
+    double *Z = nullptr;
+    int cheb = 2;
     LevelGrid gs;          // scalar nodal grid (pstride = one component plane)
     double kf[8];          // KF entries by offset pattern (da | db<<1 | dg<<2), PDEFilter.cc:472-565
     double elem_vol = 0;
@@ -48,9 +63,11 @@ k_pde_e2n(const double* __restrict__ x, double* __restrict__ rhs, double* __rest
 }
 
 // y = K u on owned planes (+ optional partial sums of u.y) ; invdiag: writes 1/diag(K) instead
+// mode 0: y = K u ; 1: y = 1/diag ; 2: y = K u + partials of u.y ; 3: y = b - K u ; 4: Chebyshev step d = s0 d + s1 dinv (b - K u), y = u + d
 __global__ void __launch_bounds__(128)
 k_helm_apply(const double* __restrict__ u, double* __restrict__ y, const __grid_constant__ Kf8 K, int nxn, int nyn, int nzl, int px,
-             long long nstride, int z0, int z1, int mode, double* __restrict__ partials) {
+             long long nstride, int z0, int z1, int mode, double* __restrict__ partials, const double* __restrict__ b = nullptr,
+             const double* __restrict__ dinv = nullptr, double* __restrict__ dd = nullptr, double s0 = 0.0, double s1 = 0.0) {
     __shared__ double red[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, z = z0 + blockIdx.z;
@@ -76,7 +93,12 @@ k_helm_apply(const double* __restrict__ u, double* __restrict__ y, const __grid_
                 }
         const long long o = z * nstride + (long long)j * px + i;
         if (mode == 1) y[o] = 1.0 / (K.v[0] * nadj);
-        else {
+        else if (mode == 3) y[o] = b[o] - acc;
+        else if (mode == 4) {
+            const double dn = s0 * dd[o] + s1 * dinv[o] * (b[o] - acc);
+            dd[o] = dn;
+            y[o] = u[o] + dn;
+        } else {
             y[o] = acc;
             dot = u[o] * acc;
         }
@@ -115,6 +137,230 @@ static int helm_apply(tob_filter_impl* h, const double* u, double* y, int mode, 
     return 0;
 }
 
+
+// ---- multigrid for the Helmholtz solve -------------------------------------------------------------------------------------
+static void helm_kf(const double d[3], double R, double* kf) {
+    for (int pat = 0; pat < 8; pat++) {
+        double m[3], k[3];
+        for (int a = 0; a < 3; a++) {
+            const bool diff = (pat >> a) & 1;
+            m[a] = diff ? d[a] / 6.0 : d[a] / 3.0;
+            k[a] = diff ? -1.0 / d[a] : 1.0 / d[a];
+        }
+        kf[pat] = R * R * (k[0] * m[1] * m[2] + m[0] * k[1] * m[2] + m[0] * m[1] * k[2]) + m[0] * m[1] * m[2];
+    }
+}
+// Gershgorin bound of D^-1 K over the 27 kinds of rows (interior / low face / high face per direction)
+static double helm_lambda_bound(const double* kf) {
+    double worst = 0.0;
+    for (int cfg = 0; cfg < 27; cfg++) {
+        const int st[3] = {cfg % 3, (cfg / 3) % 3, cfg / 9};  // 0 interior, 1 no lower neighbour, 2 no upper neighbour
+        int nadj = 1;
+        for (int a = 0; a < 3; a++) nadj *= st[a] == 0 ? 2 : 1;
+        const double diag = kf[0] * nadj;
+        double off = 0.0;
+        for (int o = 0; o < 27; o++) {
+            const int dv[3] = {o % 3 - 1, (o / 3) % 3 - 1, o / 9 - 1};
+            if (o == 13) continue;
+            bool ok = true;
+            int shared = 1, pat = 0;
+            for (int a = 0; a < 3; a++) {
+                if ((dv[a] == -1 && st[a] == 1) || (dv[a] == 1 && st[a] == 2)) ok = false;
+                if (dv[a] == 0) shared *= st[a] == 0 ? 2 : 1;  // elements on both sides along an axis the two nodes share
+                else pat |= 1 << a;
+            }
+            if (ok) off += fabs(kf[pat]) * shared;
+        }
+        worst = fmax(worst, (diag + off) / diag);
+    }
+    return worst;
+}
+
+__global__ void __launch_bounds__(128)
+k_s_restrict(const double* __restrict__ rf, double* __restrict__ rc, int nfx, int nfy, int nfzl, int ncx, int pxf, int pxc, long long nsf,
+             long long nsc, int zc0, int nzc, int gc0, int gf0) {
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    const int J = blockIdx.y, K = blockIdx.z;
+    if (I >= ncx || K >= nzc) return;
+    const int kc = zc0 + K, kf = 2 * (kc + gc0) - gf0;
+    double acc = 0.0;
+    for (int dk = -1; dk <= 1; dk++) {
+        const int z = kf + dk;
+        if (z < 0 || z >= nfzl) continue;
+        for (int dj = -1; dj <= 1; dj++) {
+            const int y = 2 * J + dj;
+            if (y < 0 || y >= nfy) continue;
+            for (int di = -1; di <= 1; di++) {
+                const int x = 2 * I + di;
+                if (x < 0 || x >= nfx) continue;
+                acc = fma((di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * (dk ? 0.5 : 1.0), rf[z * nsf + (long long)y * pxf + x], acc);
+            }
+        }
+    }
+    rc[kc * nsc + (long long)J * pxc + I] = acc;
+}
+__global__ void __launch_bounds__(128)
+k_s_prolong_add(double* __restrict__ xf, const double* __restrict__ xc, int nfx, int pxf, int pxc, long long nsf, long long nsc, int zf0,
+                int nzf, int gf0, int gc0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, k = blockIdx.z;
+    if (i >= nfx || k >= nzf) return;
+    const int kf = zf0 + k, kg = kf + gf0;
+    const int I0 = i >> 1, J0 = j >> 1, K0 = (kg >> 1) - gc0;
+    const int ni = 1 + (i & 1), nj = 1 + (j & 1), nk = 1 + (kg & 1);
+    double acc = 0.0;
+    for (int a = 0; a < nk; a++)
+        for (int b = 0; b < nj; b++)
+            for (int c = 0; c < ni; c++) acc += xc[(K0 + a) * nsc + (long long)(J0 + b) * pxc + I0 + c];
+    xf[kf * nsf + (long long)j * pxf + i] += acc / (ni * nj * nk);
+}
+__global__ void __launch_bounds__(kFlatThreads) k_s_cheb_first(double* __restrict__ x, double* __restrict__ d, const double* __restrict__ b,
+                                                               const double* __restrict__ dinv, double s1, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = s1 * dinv[i] * b[i];
+        d[i] = v;
+        x[i] = v;
+    }
+}
+
+static int lvl_apply(tob_filter_impl* h, PdeLevel& L, const double* u, double* y, int mode, const double* b, double s0, double s1) {
+    tob_ctx_impl* c = h->c;
+    const LevelGrid& g = L.g;
+    Kf8 K;
+    for (int i = 0; i < 8; i++) K.v[i] = L.kf[i];
+    dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());
+    k_helm_apply<<<grid, 128, 0, c->stream>>>(u, y, K, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.zl_own0(), g.zl_own1(), mode, c->d_partials, b,
+                                              L.dinv, L.d, s0, s1);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+// k Chebyshev-Jacobi steps on K x = b (iterate ends in L.x)
+static int pde_smooth(tob_filter_impl* h, PdeLevel& L, int k, bool zero_init, double ratio = 6.0) {
+    tob_ctx_impl* c = h->c;
+    const LevelGrid& g = L.g;
+    const double lmax = 1.02 * L.lam, lmin = L.lam / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    double *xin = L.x, *xout = L.x2;
+    for (int s = 0; s < k; s++) {
+        double s0, s1;
+        if (s == 0) { s0 = 0.0; s1 = 1.0 / theta; }
+        else {
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            s0 = rho_new * rho; s1 = 2.0 * rho_new / delta; rho = rho_new;
+        }
+        if (s == 0 && zero_init) {
+            k_s_cheb_first<<<flat_grid(c, g.own_len), kFlatThreads, 0, c->stream>>>(xin + g.own_off, L.d + g.own_off, L.b + g.own_off,
+                                                                                  L.dinv + g.own_off, s1, g.own_len);
+            c->launches++;
+            TOB_KERNEL_CHECK();
+            continue;
+        }
+        TOB_CHECK(halo_nodes(c, g, xin));
+        TOB_CHECK(lvl_apply(h, L, xin, xout, 4, L.b, s0, s1));
+        double* t = xin; xin = xout; xout = t;
+    }
+    if (xin != L.x) TOB_CHECK(vec_copy(c, L.x + g.own_off, xin + g.own_off, g.own_len));
+    return 0;
+}
+
+static int pde_vcycle(tob_filter_impl* h, int l) {
+    tob_ctx_impl* c = h->c;
+    PdeFilterState* s = h->pde;
+    PdeLevel& L = s->lv[l];
+    if (l == (int)s->lv.size() - 1) return pde_smooth(h, L, 14, true, 40.0);  // coarsest (tiny): Chebyshev over the whole spectrum of D^-1 K
+    TOB_CHECK(pde_smooth(h, L, s->cheb, true));
+    TOB_CHECK(halo_nodes(c, L.g, L.x));
+    TOB_CHECK(lvl_apply(h, L, L.x, L.r, 3, L.b, 0, 0));
+    PdeLevel& Cc = s->lv[l + 1];
+    TOB_CHECK(halo_nodes(c, L.g, L.r));
+    {
+        const LevelGrid &f = L.g, &g = Cc.g;
+        dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());
+        k_s_restrict<<<grid, 128, 0, c->stream>>>(L.r, Cc.b, f.nxn, f.nyn, f.nzl(), g.nxn, f.px, g.px, f.nstride, g.nstride, g.zl_own0(),
+                                                  g.zl_own1() - g.zl_own0(), g.gn0, f.gn0);
+        c->launches++;
+        TOB_KERNEL_CHECK();
+    }
+    TOB_CHECK(pde_vcycle(h, l + 1));
+    TOB_CHECK(halo_nodes(c, Cc.g, Cc.x));
+    {
+        const LevelGrid &f = L.g, &g = Cc.g;
+        dim3 grid(div_up(f.nxn, 128), f.nyn, f.zl_own1() - f.zl_own0());
+        k_s_prolong_add<<<grid, 128, 0, c->stream>>>(L.x, Cc.x, f.nxn, f.px, g.px, f.nstride, g.nstride, f.zl_own0(), f.zl_own1() - f.zl_own0(),
+                                                     f.gn0, g.gn0);
+        c->launches++;
+        TOB_KERNEL_CHECK();
+    }
+    return pde_smooth(h, L, s->cheb, false);
+}
+
+static int pde_mg_setup(tob_filter_impl* h) {
+    tob_ctx_impl* c = h->c;
+    PdeFilterState* s = h->pde;
+    if (getenv("TOB_PDE_MG") && atoi(getenv("TOB_PDE_MG")) == 0) return 0;
+    const LevelGrid& g0 = s->gs;
+    const int nranks = c->desc.nranks, rank = c->desc.rank;
+    // number of levels: every dimension even, every slab boundary on a coarse element boundary, coarsest >= 4 elements wide
+    int nl = 1;
+    for (; nl < 6; nl++) {
+        const int div = 1 << nl;
+        if (g0.nex % div || g0.ney % div || g0.nez % div) break;
+        if (g0.nex / div < 4 || g0.ney / div < 4 || g0.nez / div < 4) break;
+        bool ok = true;
+        for (int r = 0; r < nranks && ok; r++) {
+            int e0 = 0, e1 = 0;
+            TOB_CHECK(tob_slab_partition(g0.nzn, nranks, r, nullptr, nullptr, &e0, &e1));
+            if ((e0 % div) || (e1 % div) || (e1 - e0) / div < 1) ok = false;
+        }
+        if (!ok) break;
+    }
+    if (nl < 2) return 0;
+    s->lv.resize(nl);
+    for (int l = 0; l < nl; l++) {
+        PdeLevel& L = s->lv[l];
+        if (l == 0) {
+            L.g = g0;
+            memcpy(L.kf, s->kf, sizeof L.kf);
+            L.dinv = s->DINV;
+        } else {
+            const LevelGrid& f = s->lv[l - 1].g;
+            const int ke0 = f.ke0 / 2, ke1 = f.ke1 / 2;
+            const int kn0 = rank == 0 ? 0 : ke0 + 1, kn1 = ke1 + 1;
+            make_level_grid(L.g, f.nex / 2 + 1, f.ney / 2 + 1, f.nez / 2 + 1, 2 * f.dx, 2 * f.dy, 2 * f.dz, rank, nranks, kn0, kn1);
+            L.g.pstride = L.g.nstride;  // scalar field
+            L.g.nvec = L.g.nstride * L.g.nzl();
+            L.g.own_off = L.g.nstride * (L.g.kn0 - L.g.gn0);
+            L.g.own_len = L.g.nstride * (L.g.kn1 - L.g.kn0);
+            const double d[3] = {L.g.dx, L.g.dy, L.g.dz};
+            helm_kf(d, s->R, L.kf);
+            TOB_CUDA(cudaMalloc(&L.dinv, sizeof(double) * L.g.nvec));
+            TOB_CUDA(cudaMemsetAsync(L.dinv, 0, sizeof(double) * L.g.nvec, c->stream));
+        }
+        L.lam = helm_lambda_bound(L.kf);
+        double** vs[] = {&L.x, &L.x2, &L.b, &L.r, &L.d};
+        for (auto v : vs) {
+            TOB_CUDA(cudaMalloc(v, sizeof(double) * L.g.nvec));
+            TOB_CUDA(cudaMemsetAsync(*v, 0, sizeof(double) * L.g.nvec, c->stream));
+        }
+        if (l > 0) TOB_CHECK(lvl_apply(h, L, L.x, L.dinv, 1, nullptr, 0, 0));
+    }
+    TOB_CUDA(cudaMalloc(&s->Z, sizeof(double) * g0.nvec));
+    TOB_CUDA(cudaMemsetAsync(s->Z, 0, sizeof(double) * g0.nvec, c->stream));
+    return 0;
+}
+
+// z = V-cycle(r) on the fine scalar grid
+static int pde_precond(tob_filter_impl* h, const double* r, double* z) {
+    PdeFilterState* s = h->pde;
+    PdeLevel& L0 = s->lv[0];
+    TOB_CHECK(vec_copy(h->c, L0.b, r, L0.g.nvec));
+    TOB_CHECK(pde_vcycle(h, 0));
+    return vec_copy(h->c, z, L0.x, L0.g.nvec);
+}
+
 int pdefilter_create(tob_filter_impl* h) {
     tob_ctx_impl* c = h->c;
     auto* s = new PdeFilterState();
@@ -150,6 +396,7 @@ int pdefilter_create(tob_filter_impl* h) {
     const double v01[2] = {0.0, 1.0};
     TOB_CUDA(cudaMemcpyAsync(c->d_scalars, v01, sizeof v01, cudaMemcpyHostToDevice, c->stream));
     TOB_CHECK(helm_apply(h, s->U, s->DINV, 1, nullptr));
+    TOB_CHECK(pde_mg_setup(h));
     TOB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -179,15 +426,36 @@ int pdefilter_apply(tob_filter_impl* h, const double* x_nat, double* out_nat) {
     TOB_CHECK(vec_copy(c, s->Rr, s->B, g.nvec));
     TOB_CHECK(vec_axpby(c, s->Rr + g.own_off, s->Q + g.own_off, -1.0, 1.0, g.own_len));  // r = b - K u0
     int cur = P_S_PAIR_A, nxt = P_S_PAIR_B;
-    TOB_CHECK(pcg_update_xr(c, g, s->U, s->Rr, s->Rr, s->Rr, s->DINV, 0, 1, cur));
-    TOB_CHECK(pcg_update_p(c, g, s->P, s->Rr, s->DINV, 0, 1, 1));
+    const bool mgpc = !s->lv.empty();
+    TOB_CHECK(pcg_update_xr(c, g, s->U, s->Rr, s->Rr, s->Rr, mgpc ? nullptr : s->DINV, 0, 1, cur));  // alpha = 0: forms r.r (and r.dinv.r)
+    if (mgpc) {
+        TOB_CHECK(pde_precond(h, s->Rr, s->Z));
+        TOB_CHECK(vec_dot(c, g, s->Rr, s->Z, cur + 1));
+        TOB_CHECK(pcg_update_p(c, g, s->P, s->Z, nullptr, 0, 1, 1));
+    } else {
+        TOB_CHECK(pcg_update_p(c, g, s->P, s->Rr, s->DINV, 0, 1, 1));
+    }
     double sc[2], bb = 0;
     TOB_CHECK(read_scalars(c, P_S_BB, 1, &bb));
     TOB_CHECK(read_scalars(c, cur, 2, sc));
     const double bnorm = sqrt(bb);
     double rnorm = sqrt(sc[0]);
     const double tol = s->rtol * bnorm;
-    while (rnorm > tol && it < s->maxits) {
+    while (mgpc && rnorm > tol && it < s->maxits) {  // V-cycle-preconditioned CG: a handful of iterations, checked every time
+        TOB_CHECK(halo_nodes(c, g, s->P));
+        TOB_CHECK(helm_apply(h, s->P, s->Q, 2, &np));
+        TOB_CHECK(finalize_sum(c, np, 1, P_S_PQ, true));
+        TOB_CHECK(pcg_update_xr(c, g, s->U, s->Rr, s->P, s->Q, nullptr, cur + 1, P_S_PQ, nxt));
+        TOB_CHECK(pde_precond(h, s->Rr, s->Z));
+        TOB_CHECK(vec_dot(c, g, s->Rr, s->Z, nxt + 1));
+        TOB_CHECK(pcg_update_p(c, g, s->P, s->Z, nullptr, nxt + 1, cur + 1, 0));
+        int t = cur; cur = nxt; nxt = t;
+        it++;
+        TOB_CHECK(read_scalars(c, cur, 2, sc));
+        rnorm = sqrt(sc[0]);
+        if (!(rnorm == rnorm)) TOB_FAIL("PDE filter MG-PCG produced NaN");
+    }
+    while (!mgpc && rnorm > tol && it < s->maxits) {
         for (int k = 0; k < 5 && it < s->maxits; k++) {  // check convergence every 5 iterations
             TOB_CHECK(halo_nodes(c, g, s->P));
             TOB_CHECK(helm_apply(h, s->P, s->Q, 2, &np));
@@ -223,8 +491,14 @@ int pdefilter_apply(tob_filter_impl* h, const double* x_nat, double* out_nat) {
 void pdefilter_destroy(tob_filter_impl* h) {
     PdeFilterState* s = h->pde;
     if (!s) return;
-    double* vs[] = {s->U, s->B, s->Rr, s->P, s->Q, s->DINV, s->x_st};
+    double* vs[] = {s->U, s->B, s->Rr, s->P, s->Q, s->DINV, s->x_st, s->Z};
     for (auto v : vs) cudaFree(v);
+    for (size_t l = 0; l < s->lv.size(); l++) {
+        PdeLevel& L = s->lv[l];
+        double* ws[] = {L.x, L.x2, L.b, L.r, L.d};
+        for (auto v : ws) cudaFree(v);
+        if (l > 0) cudaFree(L.dinv);
+    }
     delete s;
     h->pde = nullptr;
 }
