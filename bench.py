@@ -146,11 +146,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def gmg_levels(c, cap=6):
+def gmg_levels(c, cap=8):
     """deepest hierarchy (<= cap levels) whose coarsening divides the grid (on N > 1 ranks the library replicates the
     levels whose slab boundaries stop being aligned, so the depth does not depend on N)"""
     nlv = cap
-    while nlv > 2 and any(d % (1 << (nlv - 1)) for d in (c["nex"], c["ney"], c["nez"])):
+    # every dimension must divide, and the coarsest grid keeps >= 2 elements per direction (it is inverted explicitly)
+    while nlv > 2 and any(d % (1 << (nlv - 1)) or (d >> (nlv - 1)) < 2 for d in (c["nex"], c["ney"], c["nez"])):
         nlv -= 1
     return nlv
 
@@ -252,8 +253,16 @@ def run_ours(args):
     c = dict(BASE, **WORKLOADS[args.workload])
 
     def make_ctx(cfg):
+        # every communicator needs its own ncclUniqueId
+        cid = None
+        if world > 1:
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            cid = bytes(t.cpu().tolist())
         return Context(cfg["nex"] + 1, cfg["ney"] + 1, cfg["nez"] + 1, xc=cfg["xc"], rank=rank, nranks=world, device=local,
-                       nccl_id=nccl_id)
+                       nccl_id=cid)
 
     ctx = make_ctx(c)
 

@@ -165,6 +165,12 @@ int tob_mma_design_change(tob_mma* h, const double* x, double* xold, double* ch)
 int tob_mma_get_restart(tob_mma* h, double* xo1, double* xo2, double* U, double* L, int* k);
 int tob_mma_set_restart(tob_mma* h, const double* xo1, const double* xo2, const double* U, const double* L, int k);
 
+/* Single-precision variant of tob_elast_spmv on the 5th-generation tensor cores (tcgen05.mma kind::tf32, fp32 accumulation
+ * in tensor memory): the smoother-grade operator ("mixed-precision smoother", BASELINE configs[4]).  Same operator
+ * (LinearElasticity.cc:510-542 + MatMult), TF32 input rounding: relative accuracy ~1e-3.  u / y fp64 at the boundary. */
+int tob_elast_spmv_tf32(tob_elast* h, const double* u, double* y);
+int tob_elast_spmv_tf32_bench(tob_elast* h, int reps, double* ms_per_apply);
+
 /* ---- diagnostics for the parity tests -------------------------------------------------------------------------------- */
 /* Levels of the multigrid hierarchy (replaces PCMGSetLevels, LinearElasticity.cc:691) and, for a Galerkin level (the R A P
  * product of PCMGSetGalerkin, :702), its assembled 27-point block stencil A[243][nz*ny*px], k = 9*offset + 3*c + c2;

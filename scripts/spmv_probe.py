@@ -39,6 +39,12 @@ for sz in a.sizes.split(","):
         ms = phys.SpMVBench(kernel=k, reps=reps)
         gbs = alg_bytes / (ms * 1e-3) / 1e9
         rec["kernels"][names[k]] = {"ms": ms, "gbs": gbs, "frac_of_measured_hbm": gbs / peaks["hbm_gbs"]}
+    if os.environ.get("TOB_PROBE_TF32"):
+        phys.SpMVtf32(u)
+        ms = phys.SpMVtf32Bench(reps=a.reps)
+        b32 = 8 * ctx.nel + 8 * ctx.ndof  # fp32 vectors, fp64 modulus as stored
+        rec["kernels"]["tc32_tcgen05_tf32"] = {"ms": ms, "gbs_fp32_bytes": b32 / (ms * 1e-3) / 1e9, "alg_bytes_fp32": b32,
+                                               "frac_of_measured_hbm": b32 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     out.setdefault("spmv", []).append(rec)
     print(json.dumps(rec), flush=True)
     phys.close(); ctx.close()

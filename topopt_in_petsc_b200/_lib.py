@@ -101,6 +101,8 @@ SIGNATURES = {
     "tob_mma_design_change": (_I, [_P, _P, _P, _PD]),
     "tob_mma_get_restart": (_I, [_P, _P, _P, _P, _P, _PI]),
     "tob_mma_set_restart": (_I, [_P, _P, _P, _P, _P, _I]),
+    "tob_elast_spmv_tf32": (_I, [_P, _P, _P]),
+    "tob_elast_spmv_tf32_bench": (_I, [_P, _I, _PD]),
     "tob_elast_gmg_nlevels": (_I, [_P, _PI]),
     "tob_elast_gmg_level_stencil": (_I, [_P, _I, _P, _PI, _PI]),
     "tob_microbench_fp64": (_I, [_P, _I, _PD]),

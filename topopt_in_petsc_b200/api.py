@@ -167,6 +167,18 @@ class LinearElasticity:
         check(self.lib.tob_elast_spmv(self.h, _ptr(u), _ptr(y)))
         return y
 
+    def SpMVtf32(self, u, y=None):
+        """single-precision tensor-core variant (tcgen05 kind::tf32); fp64 arrays at the boundary"""
+        if y is None:
+            y = np.empty(self.ctx.ndof_owned)
+        check(self.lib.tob_elast_spmv_tf32(self.h, _ptr(u), _ptr(y)))
+        return y
+
+    def SpMVtf32Bench(self, reps=20):
+        ms = C.c_double()
+        check(self.lib.tob_elast_spmv_tf32_bench(self.h, reps, C.byref(ms)))
+        return ms.value
+
     def Diag(self):
         d = np.empty(self.ctx.ndof_owned)
         check(self.lib.tob_elast_diag(self.h, d.ctypes.data))

@@ -67,6 +67,7 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
     double2* lo2 = reinterpret_cast<double2*>(pe.u_lo_ghost);
     double2* hi2 = reinterpret_cast<double2*>(pe.u_hi_ghost);
     double gam = 0.0, rr = 0.0;
+    bool remote = false;  // only the threads that stored into a neighbour need the system-scope fence
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         double2 rv = r2[i];
         if (MODE == 1) {
@@ -81,12 +82,12 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
         const double2 dv = d2[i];
         const double2 un = make_double2(dv.x * rv.x, dv.y * rv.y);
         u2[i] = un;
-        if (lo2 && i < plane2) lo2[i] = un;                              // my first owned plane = lower neighbour's top ghost
-        if (hi2 && i >= n2 - plane2) hi2[i - (n2 - plane2)] = un;        // my last owned plane = upper neighbour's bottom ghost
+        if (lo2 && i < plane2) { lo2[i] = un; remote = true; }                        // my first owned plane = lower neighbour's top ghost
+        if (hi2 && i >= n2 - plane2) { hi2[i - (n2 - plane2)] = un; remote = true; }  // my last owned plane = upper neighbour's bottom ghost
         gam = fma(rv.x, un.x, gam); gam = fma(rv.y, un.y, gam);
         rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
     }
-    if (pe.n > 1) __threadfence_system();
+    if (remote) __threadfence_system();
     gam = block_sum(gam, red);
     rr = block_sum(rr, red);
     if (threadIdx.x == 0) {

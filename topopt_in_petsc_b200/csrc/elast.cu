@@ -533,6 +533,7 @@ void elast_destroy(tob_elast_impl* h) {
     for (auto e : h->prof_ev) cudaEventDestroy(e);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     sr_destroy(h);
+    cudaFree(h->u32); cudaFree(h->y32); cudaFree(h->keT32);
     cudaFree(h->mask);
     hex8_free_operator(h->op);
     delete h;
@@ -611,6 +612,60 @@ int tob_elast_spmv(tob_elast* hh, const double* u, double* y) {
     TOB_CHECK(elast_apply(h, h->P, h->Q, EPI_Y, true, 0, nullptr, nullptr));
     TOB_CHECK(stored_to_nat_dof(c, g, h->Q, (double*)dy));
     return stage_out_finish(c, y, dy, sizeof(double) * nd);
+}
+static int tc32_buffers(tob_elast_impl* h) {
+    if (h->u32) return 0;
+    TOB_CUDA(cudaMalloc(&h->u32, sizeof(float) * h->g->nvec));
+    TOB_CUDA(cudaMalloc(&h->y32, sizeof(float) * h->g->nvec));
+    TOB_CUDA(cudaMemsetAsync(h->y32, 0, sizeof(float) * h->g->nvec, h->c->stream));
+    return 0;
+}
+/* y = N.(K (N.u)) + (1-N).u in single precision on the tensor cores (TF32 inputs, fp32 accumulation): the smoother-grade
+ * variant of tob_elast_spmv.  u / y are fp64 at the boundary (converted inside). */
+int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
+    auto* h = reinterpret_cast<tob_elast_impl*>(hh);
+    tob_ctx_impl* c = h->c;
+    const LevelGrid& g = *h->g;
+    if (!h->have_density) TOB_FAIL("tob_elast_set_density must be called before tob_elast_spmv_tf32");
+    const long long nd = 3 * g.owned_nodes();
+    const void* du; void* dy;
+    TOB_CHECK(stage_in(c, 0, u, sizeof(double) * nd, &du));
+    TOB_CHECK(stage_out_begin(c, 1, y, sizeof(double) * nd, &dy));
+    TOB_CHECK(tc32_buffers(h));
+    TOB_CHECK(vec_zero(c, h->P, g.nvec));
+    TOB_CHECK(nat_to_stored_dof(c, g, (const double*)du, h->P));
+    TOB_CHECK(halo_nodes(c, g, h->P));
+    TOB_CHECK(vec_d2f(c, h->P, h->u32, g.nvec));
+    TOB_CHECK(hex8_spmv_tc32(c, g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
+    TOB_CHECK(vec_f2d(c, h->y32, h->Q, g.nvec));
+    TOB_CHECK(stored_to_nat_dof(c, g, h->Q, (double*)dy));
+    return stage_out_finish(c, y, dy, sizeof(double) * nd);
+}
+/* times `reps` launches of the tensor-core operator (L2 flushed between launches, CUDA events around each) */
+int tob_elast_spmv_tf32_bench(tob_elast* hh, int reps, double* ms_per_apply) {
+    auto* h = reinterpret_cast<tob_elast_impl*>(hh);
+    tob_ctx_impl* c = h->c;
+    if (!h->have_density || !h->u32) TOB_FAIL("call tob_elast_spmv_tf32 once first");
+    const size_t flush_bytes = 512ull << 20;
+    TOB_CHECK(c->stage[7].reserve(flush_bytes));
+    for (int i = 0; i < 3; i++) TOB_CHECK(hex8_spmv_tc32(c, *h->g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
+    cudaEvent_t e0, e1;
+    TOB_CUDA(cudaEventCreate(&e0));
+    TOB_CUDA(cudaEventCreate(&e1));
+    double tot = 0.0;
+    for (int i = 0; i < reps; i++) {
+        TOB_CUDA(cudaMemsetAsync(c->stage[7].p, i & 0xff, flush_bytes, c->stream));
+        TOB_CUDA(cudaEventRecord(e0, c->stream));
+        TOB_CHECK(hex8_spmv_tc32(c, *h->g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
+        TOB_CUDA(cudaEventRecord(e1, c->stream));
+        TOB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        TOB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        tot += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_apply = reps ? tot / reps : 0.0;
+    return 0;
 }
 int tob_elast_diag(tob_elast* hh, double* d) {
     auto* h = reinterpret_cast<tob_elast_impl*>(hh);

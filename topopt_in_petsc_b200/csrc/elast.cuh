@@ -36,6 +36,8 @@ struct tob_elast_impl {
     long long pcg_graph_launches = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
+    // fp32 scratch of the tensor-core operator (hex8_tc32.cu)
+    float *u32 = nullptr, *y32 = nullptr, *keT32 = nullptr;
     // single-reduction Jacobi-PCG (cgsr.cuh): u = D^-1 r lives in a peer-mapped buffer (the neighbours store its ghost planes)
     PeerVec sr_u;
     CgDev* sr_cg = nullptr;

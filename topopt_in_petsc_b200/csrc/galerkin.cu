@@ -385,6 +385,89 @@ int stencil_coarse_solve(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid
     return 0;
 }
 
+
+// ---- coarsest level: explicit inverse ----------------------------------------------------------------------------------------
+// The coarsest Galerkin matrix is a few hundred dofs (6x3x3 elements -> 336): it is inverted ONCE per design iteration by an
+// in-place Gauss-Jordan sweep inside one CTA (SPD: no pivoting), and every V-cycle's coarse solve is one dense
+// matrix-vector product in one launch -- exact, hence a linear preconditioner (the round-1 fixed-count CG was neither), and
+// ~3 us instead of ~400.
+__global__ void __launch_bounds__(256) k_stencil_to_dense(const double* __restrict__ A, double* __restrict__ D, int nx, int ny, int nz, int px,
+                                                          long long nnp, int n) {
+    // one CTA per dense row (dof 3*node + c, node = i + nx (j + ny k))
+    const int row = blockIdx.x, node = row / 3, c = row % 3;
+    const int i = node % nx, j = (node / nx) % ny, k = node / (nx * ny);
+    const long long nn = ((long long)k * ny + j) * px + i;
+    for (int col = threadIdx.x; col < n; col += blockDim.x) D[(long long)row * n + col] = 0.0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 81; t += blockDim.x) {
+        const int o = t / 3, c2 = t % 3;
+        const int di = o % 3 - 1, dj = (o / 3) % 3 - 1, dk = o / 9 - 1;
+        const int ii = i + di, jj = j + dj, kk = k + dk;
+        if (ii < 0 || ii >= nx || jj < 0 || jj >= ny || kk < 0 || kk >= nz) continue;
+        D[(long long)row * n + 3 * (ii + nx * (jj + ny * kk)) + c2] = A[(long long)(o * 9 + 3 * c + c2) * nnp + nn];
+    }
+}
+__global__ void __launch_bounds__(1024) k_dense_invert(double* __restrict__ D, int n) {
+    extern __shared__ double sm[];  // rowk[n], colk[n]
+    double* rowk = sm;
+    double* colk = sm + n;
+    for (int k = 0; k < n; k++) {
+        const double p = 1.0 / D[(long long)k * n + k];
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            rowk[j] = (j == k) ? p : D[(long long)k * n + j] * p;
+            colk[j] = D[(long long)j * n + k];  // a_jk, the multiplier of row j
+        }
+        __syncthreads();
+        for (long long e = threadIdx.x; e < (long long)n * n; e += blockDim.x) {
+            const int i = (int)(e / n), j = (int)(e % n);
+            double v;
+            if (i == k) v = rowk[j];
+            else if (j == k) v = -colk[i] * p;
+            else v = D[e] - colk[i] * rowk[j];
+            D[e] = v;
+        }
+        __syncthreads();
+    }
+}
+// x = Ainv b with b, x in the stored nodal layout; one CTA, one warp per row round-robin
+__global__ void __launch_bounds__(1024) k_dense_solve(const double* __restrict__ Ainv, const double* __restrict__ b, double* __restrict__ x, int n,
+                                                      int nx, int ny, int px, long long nstride, long long pstride) {
+    extern __shared__ double sb[];  // b in dense dof order
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+        const int node = d / 3, c = d % 3, i = node % nx, j = (node / nx) % ny, k = node / (nx * ny);
+        sb[d] = b[(long long)k * pstride + c * nstride + (long long)j * px + i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int row = warp; row < n; row += nw) {
+        double s = 0.0;
+        for (int col = lane; col < n; col += 32) s = fma(Ainv[(long long)row * n + col], sb[col], s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const int node = row / 3, c = row % 3, i = node % nx, j = (node / nx) % ny, k = node / (nx * ny);
+            x[(long long)k * pstride + c * nstride + (long long)j * px + i] = s;
+        }
+    }
+}
+
+int stencil_dense_setup(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S) {
+    const int n = 3 * g.nxn * g.nyn * g.nzn;
+    if (n > kDenseCoarseMax) return 0;  // too large: the caller keeps the iterative coarse solve
+    if (!S.Ainv) TOB_CUDA(cudaMalloc(&S.Ainv, sizeof(double) * (size_t)n * n));
+    S.ndense = n;
+    k_stencil_to_dense<<<n, 256, 0, c->stream>>>(S.A, S.Ainv, g.nxn, g.nyn, g.nzn, g.px, S.nnp, n);
+    k_dense_invert<<<1, 1024, sizeof(double) * 2 * n, c->stream>>>(S.Ainv, n);
+    c->launches += 2;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+int stencil_dense_solve(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid& g, const double* b, double* x) {
+    k_dense_solve<<<1, 1024, sizeof(double) * S.ndense, c->stream>>>(S.Ainv, b, x, S.ndense, g.nxn, g.nyn, g.px, g.nstride, g.pstride);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
 // ---- level management --------------------------------------------------------------------------------------------------------
 int stencil_alloc(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S) {
     S.nnp = (long long)g.nzn * g.nyn * g.px;
@@ -399,7 +482,7 @@ int stencil_alloc(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S) {
     return 0;
 }
 void stencil_free(StencilLevel& S) {
-    cudaFree(S.A); cudaFree(S.coef); cudaFree(S.lam); cudaFree(S.its); cudaFree(S.pv); cudaFree(S.pt); cudaFree(S.pw); cudaFree(S.M);
+    cudaFree(S.A); cudaFree(S.coef); cudaFree(S.lam); cudaFree(S.its); cudaFree(S.pv); cudaFree(S.pt); cudaFree(S.pw); cudaFree(S.M); cudaFree(S.Ainv);
     S = StencilLevel();
 }
 

@@ -12,9 +12,14 @@ struct StencilLevel {
     int* its = nullptr;      // iterations of the last single-CTA coarse solve
     double *pv = nullptr, *pt = nullptr, *pw = nullptr;  // power-iteration work vectors
     bool pv_init = false;
+    double* Ainv = nullptr;  // coarsest level: explicit inverse (dense, ndense x ndense), refreshed with the operator
+    int ndense = 0;
     double* M = nullptr;     // [8][24][24] Q_child^T KE Q_child (level assembled from a matrix-free parent)
 };
 
+constexpr int kDenseCoarseMax = 1024;  // dofs up to which the coarsest level is inverted explicitly
+int stencil_dense_setup(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S);
+int stencil_dense_solve(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid& g, const double* b, double* x);
 void galerkin_child_matrices(const double* KE_fine, double* M);
 int stencil_alloc(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S);
 void stencil_free(StencilLevel& S);

@@ -47,6 +47,7 @@ struct GmgHierarchy {
     double *cp = nullptr, *cq = nullptr;
     // CUDA graph of one V-cycle
     bool warm = false;
+    bool timed = false;
     cudaGraphExec_t graph_exec = nullptr;
     const double* graph_r = nullptr;
     double* graph_z = nullptr;
@@ -226,8 +227,9 @@ static int coarse_solve(tob_elast_impl* h, GmgLevel& L, int its) {
     tob_ctx_impl* c = h->c;
     GmgHierarchy* mg = h->mg;
     const LevelGrid& g = L.g;
-    if (L.stencil)  // Jacobi-PCG to a relative residual inside one CTA: no launches, no host, (almost) exact -> linear preconditioner
-        return stencil_coarse_solve(c, L.S, g, L.dinv, L.b, L.x, L.r, mg->cp, mg->cq, 1.0e-6, 40 * its);
+    if (L.stencil && L.S.ndense) return stencil_dense_solve(c, L.S, g, L.b, L.x);  // explicit inverse: one launch, exact
+    if (L.stencil)  // too large to invert: Jacobi-PCG to a relative residual inside one CTA (no launches, no host)
+        return stencil_coarse_solve(c, L.S, g, L.dinv, L.b, L.x, L.r, mg->cp, mg->cq, 1.0e-4, 20 * its);
     TOB_CHECK(vec_zero(c, L.x, g.nvec));
     TOB_CHECK(vec_copy(c, L.r, L.b, g.nvec));
     int cur = G_S_PAIR_A, nxt = G_S_PAIR_B, np = 0;
@@ -247,11 +249,25 @@ static int coarse_solve(tob_elast_impl* h, GmgLevel& L, int its) {
     return 0;
 }
 
+// TOB_GMG_TIMING=1: one eager V-cycle per solve is bracketed level by level with CUDA events and printed (diagnostics for the
+// latency budget of the coarse levels)
+static std::vector<cudaEvent_t> g_tev;
+static bool g_timing = false;
+static void tmark(tob_ctx_impl* c) {
+    if (!g_timing) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    g_tev.push_back(e);
+}
+
 static int vcycle(tob_elast_impl* h, int l) {
     tob_ctx_impl* c = h->c;
     GmgHierarchy* mg = h->mg;
     GmgLevel& L = mg->lv[l];
     const int nl = (int)mg->lv.size();
+    tmark(c);  // entry of level l (2 marks per level: entry, and before returning)
+    struct Exit { tob_ctx_impl* c; ~Exit() { tmark(c); } } exit_mark{c};
     if (l == mg->dI) {
         // last distributed level: hand the problem to its replicated twin and take back my slab of the answer
         GmgLevel& R = mg->lv[l + 1];
@@ -307,6 +323,35 @@ int gmg_vcycle(tob_elast_impl* h, const double* r, double* z) {
         c->launches += mg->graph_launches;
         return 0;
     }
+    if (getenv("TOB_GMG_TIMING") && mg->warm && !mg->timed) {
+        mg->timed = true;
+        g_timing = true;
+        g_tev.clear();
+        int rc0 = vec_copy(c, L0.b, r, L0.g.nvec);
+        if (!rc0) rc0 = vcycle(h, 0);
+        g_timing = false;
+        cudaStreamSynchronize(c->stream);
+        if (c->desc.rank == 0) {
+            // marks: entry(0) entry(1) ... entry(n-1) exit(n-1) exit(n-2) ... exit(0)
+            const int nlv = (int)mg->lv.size();
+            float tot = 0;
+            cudaEventElapsedTime(&tot, g_tev.front(), g_tev.back());
+            printf("[gmg timing] V-cycle %.1f us:", tot * 1e3);
+            for (int l = 0; l < nlv && (int)g_tev.size() == 2 * nlv; l++) {
+                float down = 0, up = 0;
+                if (l + 1 < nlv) {
+                    cudaEventElapsedTime(&down, g_tev[l], g_tev[l + 1]);
+                    cudaEventElapsedTime(&up, g_tev[2 * nlv - 2 - l], g_tev[2 * nlv - 1 - l]);
+                } else cudaEventElapsedTime(&down, g_tev[l], g_tev[l + 1]);
+                printf("  L%d(%dx%dx%d%s) %.1f+%.1f", l, mg->lv[l].g.nex, mg->lv[l].g.ney, mg->lv[l].g.nez, mg->lv[l].stencil ? ",G" : "", down * 1e3, up * 1e3);
+            }
+            printf("\n");
+            fflush(stdout);
+        }
+        for (auto e : g_tev) cudaEventDestroy(e);
+        g_tev.clear();
+        if (rc0) return rc0;
+    }
     const bool capture = mg->warm && h->opts.verbose != 2;
     long long l0 = c->launches;
     if (capture) TOB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -357,6 +402,10 @@ int gmg_update(tob_elast_impl* h) {
         if (C.stencil) {  // Galerkin product P^T A P (LinearElasticity.cc:702), redone with every new design (:198-200)
             if (F.stencil) TOB_CHECK(stencil_assemble_from_stencil(c, f, F.S, g, C.mask, C.S));
             else TOB_CHECK(stencil_assemble_from_mf(c, f, F.E, F.op.KE, g, C.mask, C.S));
+            if (l + 1 == mg->lv.size()) {  // coarsest level: explicit inverse when it is small enough
+                TOB_CHECK(stencil_dense_setup(c, g, C.S));
+                if (C.S.ndense) continue;
+            }
             TOB_CHECK(stencil_finish(c, g, C.S, C.dinv, mg->lam_ratio, std::max(1, h->opts.cheb_degree), 8));
             continue;
         }

@@ -56,6 +56,12 @@ struct SpmvArgs {
 // sums written to ctx->d_partials for EPI_DOT / EPI_RESID (0 otherwise).
 int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const SpmvArgs& a, int* nparts);
 
+// single-precision operator on the tensor cores (hex8_tc32.cu: tcgen05.mma kind::tf32, accumulators in tensor memory)
+int hex8_spmv_tc32(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const float* u32, float* y32, const double* E,
+                   const unsigned char* mask, float** keT_cache);
+int vec_d2f(tob_ctx_impl* c, const double* a, float* b, long long n);
+int vec_f2d(tob_ctx_impl* c, const float* a, double* b, long long n);
+
 // dinv = 1/diag(A) (1 at clamped dofs), stored layout
 int hex8_diag_inv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const double* E,
                   const unsigned char* mask, double* dinv, bool invert);
