@@ -87,6 +87,7 @@ int elast_set_density(tob_elast_impl* h, const double* xphys_nat_dev, double Emi
     TOB_CHECK(hex8_diag_inv(c, g, h->op, h->E_st, h->mask, h->DINV, true));
     h->Emin = Emin; h->Emax = Emax; h->penal = penal;
     h->have_density = true;
+    h->E32_valid = false;
     if (h->mg) TOB_CHECK(gmg_update(h));
     return 0;
 }
@@ -533,7 +534,7 @@ void elast_destroy(tob_elast_impl* h) {
     for (auto e : h->prof_ev) cudaEventDestroy(e);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     sr_destroy(h);
-    cudaFree(h->u32); cudaFree(h->y32); cudaFree(h->keT32);
+    cudaFree(h->u32); cudaFree(h->y32); cudaFree(h->keT32); cudaFree(h->x4); cudaFree(h->y4); cudaFree(h->E32); cudaFree(h->tcB);
     cudaFree(h->mask);
     hex8_free_operator(h->op);
     delete h;
@@ -620,6 +621,25 @@ static int tc32_buffers(tob_elast_impl* h) {
     TOB_CUDA(cudaMemsetAsync(h->y32, 0, sizeof(float) * h->g->nvec, h->c->stream));
     return 0;
 }
+}  // extern "C"
+// buffers / operand blocks / fp32 modulus of the generation-2 tensor-core operator
+int tob::tc2_prepare(tob_elast_impl* h) {
+    const LevelGrid& g = *h->g;
+    const long long nn = (long long)g.nxn * g.nyn * g.nzl();
+    if (!h->x4) {
+        TOB_CUDA(cudaMalloc(&h->x4, sizeof(float4) * nn));
+        TOB_CUDA(cudaMalloc(&h->y4, sizeof(float4) * nn));
+        TOB_CUDA(cudaMemsetAsync(h->y4, 0, sizeof(float4) * nn, h->c->stream));
+        TOB_CUDA(cudaMalloc(&h->E32, sizeof(float) * g.evec));
+        TOB_CHECK(tc2_build_B(h->op, &h->tcB));
+    }
+    if (!h->E32_valid) {
+        TOB_CHECK(vec_d2f(h->c, h->E_st, h->E32, g.evec));
+        h->E32_valid = true;
+    }
+    return 0;
+}
+extern "C" {
 /* y = N.(K (N.u)) + (1-N).u in single precision on the tensor cores (TF32 inputs, fp32 accumulation): the smoother-grade
  * variant of tob_elast_spmv.  u / y are fp64 at the boundary (converted inside). */
 int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
@@ -635,9 +655,20 @@ int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
     TOB_CHECK(vec_zero(c, h->P, g.nvec));
     TOB_CHECK(nat_to_stored_dof(c, g, (const double*)du, h->P));
     TOB_CHECK(halo_nodes(c, g, h->P));
-    TOB_CHECK(vec_d2f(c, h->P, h->u32, g.nvec));
-    TOB_CHECK(hex8_spmv_tc32(c, g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
-    TOB_CHECK(vec_f2d(c, h->y32, h->Q, g.nvec));
+    const int gen = getenv("TOB_TC32_GEN") ? atoi(getenv("TOB_TC32_GEN")) : 2;
+    if (gen == 1) {
+        TOB_CHECK(vec_d2f(c, h->P, h->u32, g.nvec));
+        TOB_CHECK(hex8_spmv_tc32(c, g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
+        TOB_CHECK(vec_f2d(c, h->y32, h->Q, g.nvec));
+    } else {
+        // generation 2 works on pre-masked node-interleaved fp32 vectors (the smoother's own layout)
+        TOB_CHECK(tc2_prepare(h));
+        TOB_CHECK(vec_pointwise_mult(c, h->Z, h->P, h->NFREE, g.nvec));
+        TOB_CHECK(vec_st_to_v4(c, g, h->Z, h->x4));
+        TOB_CHECK(hex8_tc32b(c, g, h->tcB, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f));
+        TOB_CHECK(vec_v4_to_st(c, g, h->y4, h->Q));
+        TOB_CHECK(vec_restore_fixed(c, h->Q + g.own_off, h->P + g.own_off, h->NFREE + g.own_off, g.own_len));
+    }
     TOB_CHECK(stored_to_nat_dof(c, g, h->Q, (double*)dy));
     return stage_out_finish(c, y, dy, sizeof(double) * nd);
 }
@@ -645,10 +676,15 @@ int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
 int tob_elast_spmv_tf32_bench(tob_elast* hh, int reps, double* ms_per_apply) {
     auto* h = reinterpret_cast<tob_elast_impl*>(hh);
     tob_ctx_impl* c = h->c;
-    if (!h->have_density || !h->u32) TOB_FAIL("call tob_elast_spmv_tf32 once first");
+    const int gen = getenv("TOB_TC32_GEN") ? atoi(getenv("TOB_TC32_GEN")) : 2;
+    if (!h->have_density || (gen == 1 ? !h->u32 : !h->x4)) TOB_FAIL("call tob_elast_spmv_tf32 once first");
     const size_t flush_bytes = 512ull << 20;
     TOB_CHECK(c->stage[7].reserve(flush_bytes));
-    for (int i = 0; i < 3; i++) TOB_CHECK(hex8_spmv_tc32(c, *h->g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
+    auto apply = [&]() -> int {
+        if (gen == 1) return hex8_spmv_tc32(c, *h->g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32);
+        return hex8_tc32b(c, *h->g, h->tcB, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f);
+    };
+    for (int i = 0; i < 3; i++) TOB_CHECK(apply());
     cudaEvent_t e0, e1;
     TOB_CUDA(cudaEventCreate(&e0));
     TOB_CUDA(cudaEventCreate(&e1));
@@ -656,7 +692,7 @@ int tob_elast_spmv_tf32_bench(tob_elast* hh, int reps, double* ms_per_apply) {
     for (int i = 0; i < reps; i++) {
         TOB_CUDA(cudaMemsetAsync(c->stage[7].p, i & 0xff, flush_bytes, c->stream));
         TOB_CUDA(cudaEventRecord(e0, c->stream));
-        TOB_CHECK(hex8_spmv_tc32(c, *h->g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
+        TOB_CHECK(apply());
         TOB_CUDA(cudaEventRecord(e1, c->stream));
         TOB_CUDA(cudaEventSynchronize(e1));
         float ms = 0;

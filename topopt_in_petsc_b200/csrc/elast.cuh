@@ -38,6 +38,9 @@ struct tob_elast_impl {
     int prof_used = 0;
     // fp32 scratch of the tensor-core operator (hex8_tc32.cu)
     float *u32 = nullptr, *y32 = nullptr, *keT32 = nullptr;
+    float4 *x4 = nullptr, *y4 = nullptr;
+    float *E32 = nullptr, *tcB = nullptr;
+    bool E32_valid = false;
     // single-reduction Jacobi-PCG (cgsr.cuh): u = D^-1 r lives in a peer-mapped buffer (the neighbours store its ghost planes)
     PeerVec sr_u;
     CgDev* sr_cg = nullptr;
@@ -49,6 +52,7 @@ struct tob_elast_impl {
     long long sr_graph_launches = 0;
 };
 int elast_profile_collect(tob_elast_impl* h);
+int tc2_prepare(tob_elast_impl* h);  // buffers / operand blocks / fp32 modulus of the tensor-core operator (elast.cu)
 
 int elast_create(tob_ctx_impl* c, double nu, const tob_solver_opts* opts, tob_elast_impl** out);
 void elast_destroy(tob_elast_impl* h);

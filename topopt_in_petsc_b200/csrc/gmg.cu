@@ -45,6 +45,9 @@ struct GmgHierarchy {
     std::vector<size_t> gn_off, gn_cnt, ge_off, ge_cnt, gm_off, gm_cnt;  // per-rank chunks of the gather (bytes)
     // coarsest-level PCG vectors
     double *cp = nullptr, *cq = nullptr;
+    // mixed-precision smoother on the finest level (hex8_tc32.cu generation 2, tcgen05 TF32): node-interleaved fp32 vectors
+    bool tf32 = false;
+    float4 *xa4 = nullptr, *xb4 = nullptr, *b4 = nullptr, *d4 = nullptr, *dinv4 = nullptr;
     // CUDA graph of one V-cycle
     bool warm = false;
     bool timed = false;
@@ -183,11 +186,64 @@ static int level_apply(tob_elast_impl* h, GmgLevel& L, const SpmvArgs& a0, int* 
     return hex8_spmv(h->c, L.g, L.op, a, nparts);
 }
 
+__global__ void __launch_bounds__(kFlatThreads) k_cheb_first4(float4* __restrict__ x, float4* __restrict__ d, const float4* __restrict__ b,
+                                                              const float4* __restrict__ dinv, float s1, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float4 bv = b[i], dv = dinv[i];
+        const float4 v = make_float4(s1 * dv.x * bv.x, s1 * dv.y * bv.y, s1 * dv.z * bv.z, 0.0f);
+        d[i] = v;
+        x[i] = v;
+    }
+}
+
+// The same Chebyshev-Jacobi sweep on the finest level in single precision on the tensor cores: every step is ONE launch of
+// k_hex8_tc32b (operator + recurrence + new iterate).  The iterate enters / leaves in fp64 (converted), so the rest of the
+// V-cycle -- residual, transfers, coarse levels -- and the outer PCG stay fp64.
+static int cheb_smooth_tf32(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    const LevelGrid& g = L.g;
+    const long long nn = (long long)g.nxn * g.nyn * g.nzl();
+    TOB_CHECK(tc2_prepare(h));
+    if (!mg->xa4) {
+        float4** vs[] = {&mg->xa4, &mg->xb4, &mg->b4, &mg->d4, &mg->dinv4};
+        for (auto v : vs) {
+            TOB_CUDA(cudaMalloc(v, sizeof(float4) * nn));
+            TOB_CUDA(cudaMemsetAsync(*v, 0, sizeof(float4) * nn, c->stream));
+        }
+    }
+    const double lmax = 1.02 * mg->lam_max, lmin = mg->lam_max / mg->lam_ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    TOB_CHECK(vec_st_to_v4(c, g, L.b, mg->b4));
+    TOB_CHECK(vec_st_to_v4(c, g, L.dinv, mg->dinv4));
+    float4 *xin = mg->xa4, *xout = mg->xb4;
+    if (!zero_init) TOB_CHECK(vec_st_to_v4(c, g, L.x, xin));
+    for (int s = 0; s < k; s++) {
+        double s0, s1;
+        if (s == 0) { s0 = 0.0; s1 = 1.0 / theta; }
+        else {
+            const double rho_new = 1.0 / (2.0 * sigma - rho);
+            s0 = rho_new * rho; s1 = 2.0 * rho_new / delta; rho = rho_new;
+        }
+        if (s == 0 && zero_init) {
+            k_cheb_first4<<<flat_grid(c, nn), kFlatThreads, 0, c->stream>>>(xin, mg->d4, mg->b4, mg->dinv4, (float)s1, nn);
+            c->launches++;
+            TOB_KERNEL_CHECK();
+            continue;
+        }
+        TOB_CHECK(hex8_tc32b(c, g, h->tcB, xin, xout, h->E32, L.mask, 1, mg->b4, mg->dinv4, mg->d4, (float)s0, (float)s1));
+        float4* t = xin; xin = xout; xout = t;
+    }
+    return vec_v4_to_st(c, g, xin, L.x);
+}
+
 // k Chebyshev-Jacobi steps on A x = b.  zero_init: x is taken as 0 (saves the first SpMV).
 // The iterate ends in L.x (ping-pong with L.x2).
 static int cheb_smooth(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
     tob_ctx_impl* c = h->c;
     GmgHierarchy* mg = h->mg;
+    if (mg->tf32 && &L == &mg->lv[0] && !L.stencil) return cheb_smooth_tf32(h, L, k, zero_init);
     const double lmax = 1.02 * mg->lam_max, lmin = mg->lam_max / mg->lam_ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
@@ -454,6 +510,9 @@ int gmg_setup(tob_elast_impl* h) {
         dI = std::min(aligned, small);
     }
     mg->dI = dI;
+    // TOB_GMG_TF32=1: finest-level smoothing in single precision on the tensor cores (one rank; the halo of the interleaved
+    // fp32 vectors is not wired yet)
+    mg->tf32 = getenv("TOB_GMG_TF32") && atoi(getenv("TOB_GMG_TF32")) != 0 && nranks == 1;
     const int ndist = dI >= 0 ? dI + 1 : nres;       // distributed levels (single rank: all of them)
     const int nl = dI >= 0 ? ndist + (nres - dI) : nres;
     mg->lv.resize(nl);
@@ -562,6 +621,7 @@ void gmg_destroy(tob_elast_impl* h) {
     }
     cudaFree(mg->cp);
     cudaFree(mg->cq);
+    cudaFree(mg->xa4); cudaFree(mg->xb4); cudaFree(mg->b4); cudaFree(mg->d4); cudaFree(mg->dinv4);
     delete mg;
     h->mg = nullptr;
 }

@@ -59,6 +59,12 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
 // single-precision operator on the tensor cores (hex8_tc32.cu: tcgen05.mma kind::tf32, accumulators in tensor memory)
 int hex8_spmv_tc32(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const float* u32, float* y32, const double* E,
                    const unsigned char* mask, float** keT_cache);
+// generation 2 (implicit im2col through overlapping UMMA descriptors) on node-interleaved fp32 vectors ("V4": float4 per node)
+int tc2_build_B(const Hex8Operator& op, float** dB);
+int hex8_tc32b(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float4* x4, float4* y4, const float* E32, const unsigned char* mask,
+               int epi, const float4* b4, const float4* dinv4, float4* d4, float s0, float s1);
+int vec_st_to_v4(tob_ctx_impl* c, const LevelGrid& g, const double* st, float4* v4);
+int vec_v4_to_st(tob_ctx_impl* c, const LevelGrid& g, const float4* v4, double* st);
 int vec_d2f(tob_ctx_impl* c, const double* a, float* b, long long n);
 int vec_f2d(tob_ctx_impl* c, const float* a, double* b, long long n);
 

@@ -241,4 +241,254 @@ int hex8_spmv_tc32(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, 
     return 0;
 }
 
+
+// =========================================================================================================================
+// Generation 2: no gather, no scatter -- the tensor core reads the NODAL planes directly.
+//
+// Store the fp32 vector node-interleaved ("V4": one float4 = (ux, uy, uz, 0) per node, [z][y][x]).  A TMA box of
+// (8+2) x (16+2) nodes of one plane lands in shared memory as [18][10] float4.  For a fixed corner offset (a', b', g') the
+// values "node I + offset" of the 8 x-consecutive nodes I form exactly one canonical K-major core matrix (8 rows x 16 B,
+// rows 16 B apart), row groups (next y) are one tile row = 160 B apart: so the A operand of
+//     D_s[I][c] = sum_{a',b',g',c'} u[I - s + (a',b',g')][c'] * KE[(s,c), ((a',b',g'),c')]            (s = (a,b,g): element I - s)
+// is a plain UMMA shared-memory descriptor into the plane tile: start = tile + ((1-b+b')*10 + (1-a)) * 16 B, LBO = 16 B
+// (the a' = 0 / 1 chunks of a K = 8 step OVERLAP in memory), SBO = 160 B.  The modulus cannot be folded into the operand
+// (it belongs to the element, not to the node), so the eight per-element products stay separate TMEM accumulators
+// (8 x 16 columns) and each thread -- one node -- finishes  y_I = sum_s E_{I-s} D_s[I]  with 24 FMAs, adds the Chebyshev
+// update if asked, and writes its node once.  Per output plane of 128 nodes: 32 tcgen05.mma (M 128, N 16, K 8), one commit,
+// 8 tcgen05.ld per thread; shared memory sees only the TMA writes.  No CUDA-core gather/scatter, no atomics, no tile overlap.
+// =========================================================================================================================
+constexpr int T2_X = 8, T2_Y = 16;                 // output nodes per plane per CTA (= 128 = UMMA M)
+constexpr int T2_PX = T2_X + 2, T2_PY = T2_Y + 2;  // plane tile with halo
+constexpr int T2_SLOT = ((T2_PX * T2_PY * 16 + 127) / 128) * 128;
+constexpr int T2_B_BYTES = 32 * 512;               // 8 shifts x 4 K-steps x (2 chunks x 16 rows x 16 B)
+
+struct Tc2Params {
+    float4* y;                 // V4 output (EPI 0: A x; EPI 1: x + d)
+    const float* E32;          // element modulus, fp32, stored element layout
+    const unsigned char* mask;
+    const float* B;            // [32][2][16][4] operand blocks (host-prepared from KE)
+    const float4* b;           // EPI 1: right-hand side
+    const float4* dinv;        // EPI 1: 1/diag
+    float4* d;                 // EPI 1: Chebyshev direction (in/out)
+    float s0, s1;
+    int nxn, nyn, nzl, pe, pm;
+    long long estride, mstride;
+    int zout0, zout1, zchunk;
+    int epi;
+};
+
+__global__ void __launch_bounds__(128)
+k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc2Params P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;                    // operand blocks of KE
+    unsigned char* sP = smem + T2_B_BYTES;       // 4 plane slots
+    __shared__ __align__(8) uint64_t full[4];
+    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int ix = t & (T2_X - 1), iy = t >> 3;
+    const int gi = blockIdx.x * T2_X + ix, gj = blockIdx.y * T2_Y + iy;
+    const int z0 = P.zout0 + blockIdx.z * P.zchunk, z1 = min(z0 + P.zchunk, P.zout1);
+    if (z0 >= z1) return;
+
+    for (int idx = t; idx < T2_B_BYTES / 16; idx += 128) reinterpret_cast<float4*>(sB)[idx] = reinterpret_cast<const float4*>(P.B)[idx];
+    if (t == 0) {
+        for (int s = 0; s < 4; s++) mbar_init(&full[s], 1);
+        mbar_init(&mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sB was written through the generic proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    // D = F32, A = B = TF32, K-major both, N = 16, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (2u << 17) | (8u << 24);
+    const uint32_t sB_addr = smem_u32(sB), sP_addr = smem_u32(sP);
+
+    auto issue_plane = [&](int pz) {  // TMA: plane pz of this tile (with halo) -> slot pz & 3 (outside the grid: zeros)
+        const int s = pz & 3;
+        mbar_expect_tx(&full[s], T2_PX * T2_PY * 16);
+        tma_load_4d(sP + s * T2_SLOT, &tmX, &full[s], 0, (int)blockIdx.x * T2_X - 1, (int)blockIdx.y * T2_Y - 1, pz);
+    };
+    if (t == 0) {
+        for (int pz = z0 - 1; pz <= z0 + 2 && pz <= z1; pz++) issue_plane(pz);
+    }
+    // modulus of the 4 elements (ix - a, iy - b) of a layer
+    auto load_E = [&](int layer, float (&Ev)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int ei = gi - (q & 1), ej = gj - (q >> 1);
+            Ev[q] = (layer >= 0 && layer < P.nzl - 1 && ei >= 0 && ei < P.nxn - 1 && ej >= 0 && ej < P.nyn - 1)
+                        ? P.E32[(long long)layer * P.estride + (long long)ej * P.pe + ei] : 0.0f;
+        }
+    };
+    float Elo[4], Ehi[4];  // layers z - 1 (g = 1) and z (g = 0)
+    load_E(z0 - 1, Elo);
+    uint32_t mphase = 0;
+    for (int z = z0; z < z1; z++) {
+        if (t == 0) {
+            // planes z - 1, z, z + 1 must have landed (phase of a slot: one completion per 4 planes)
+            for (int pz = z - 1; pz <= z + 1; pz++) mbar_wait(&full[pz & 3], (uint32_t)(((pz - (z0 - 1)) >> 2) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const int a = s & 1, b = (s >> 1) & 1, g = s >> 2;
+#pragma unroll
+                for (int st = 0; st < 4; st++) {
+                    const int bp = st & 1, gp = st >> 1;
+                    const int pz = z - g + gp;
+                    const uint32_t aaddr = sP_addr + (uint32_t)((pz & 3) * T2_SLOT + ((1 - b + bp) * T2_PX + (1 - a)) * 16);
+                    const uint64_t da = tc_smem_desc(aaddr, 16, T2_PX * 16);
+                    const uint64_t db = tc_smem_desc(sB_addr + (uint32_t)((s * 4 + st) * 512), 256, 128);
+                    const uint32_t acc = st > 0;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem + (uint32_t)(16 * s)), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done)) : "memory");
+        }
+        load_E(z, Ehi);
+        // my own nodal value (Dirichlet pass-through / Chebyshev update) sits in the plane tile; read it before the slot is recycled
+        float4 xo;
+        {
+            // the tile of plane z has landed for thread 0 only; everybody else learns it through mma_done below, so read afterwards
+        }
+        mbar_wait(&mma_done, mphase);
+        mphase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        mbar_wait(&full[z & 3], (uint32_t)(((z - (z0 - 1)) >> 2) & 1));  // (already complete: makes the TMA writes of plane z visible to me)
+        xo = *reinterpret_cast<const float4*>(sP + (z & 3) * T2_SLOT + ((iy + 1) * T2_PX + ix + 1) * 16);
+        float acc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            uint32_t r0, r1, r2, r3;
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(16 * s);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const float Es = (s >> 2) ? Elo[s & 3] : Ehi[s & 3];
+            acc[0] = fmaf(Es, __uint_as_float(r0), acc[0]);
+            acc[1] = fmaf(Es, __uint_as_float(r1), acc[1]);
+            acc[2] = fmaf(Es, __uint_as_float(r2), acc[2]);
+            (void)r3;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (gi < P.nxn && gj < P.nyn) {
+            const unsigned char m = P.mask[(long long)z * P.mstride + (long long)gj * P.pm + gi];
+            const float xs[3] = {xo.x, xo.y, xo.z};
+            float au[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) au[c] = ((m >> c) & 1) ? xs[c] : acc[c];
+            const long long o = ((long long)z * P.nyn + gj) * P.nxn + gi;
+            if (P.epi == 0) {
+                P.y[o] = make_float4(au[0], au[1], au[2], 0.0f);
+            } else {
+                const float4 bv = P.b[o], dv = P.dinv[o], dd = P.d[o];
+                const float d0 = P.s0 * dd.x + P.s1 * dv.x * (bv.x - au[0]);
+                const float d1 = P.s0 * dd.y + P.s1 * dv.y * (bv.y - au[1]);
+                const float d2 = P.s0 * dd.z + P.s1 * dv.z * (bv.z - au[2]);
+                P.d[o] = make_float4(d0, d1, d2, 0.0f);
+                P.y[o] = make_float4(xo.x + d0, xo.y + d1, xo.z + d2, 0.0f);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) Elo[q] = Ehi[q];
+        __syncthreads();  // every thread is done with TMEM and with the tile of plane z - 1: recycle its slot
+        if (t == 0 && z + 3 <= z1) issue_plane(z + 3);
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+}
+
+// ---- V4 (node-interleaved fp32) <-> stored fp64 layout ----------------------------------------------------------------------
+__global__ void k_st_to_v4(const double* __restrict__ st, float4* __restrict__ v4, int nxn, int nyn, int nzl, int px, long long nstride,
+                           long long pstride) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long long)nxn * nyn * nzl) return;
+    const int i = n % nxn, j = (n / nxn) % nyn, k = n / ((long long)nxn * nyn);
+    const long long o = (long long)k * pstride + (long long)j * px + i;
+    v4[n] = make_float4((float)st[o], (float)st[o + nstride], (float)st[o + 2 * nstride], 0.0f);
+}
+__global__ void k_v4_to_st(const float4* __restrict__ v4, double* __restrict__ st, int nxn, int nyn, int nzl, int px, long long nstride,
+                           long long pstride, int z0, int z1) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long long)nxn * nyn * nzl) return;
+    const int i = n % nxn, j = (n / nxn) % nyn, k = n / ((long long)nxn * nyn);
+    if (k < z0 || k >= z1) return;
+    const long long o = (long long)k * pstride + (long long)j * px + i;
+    const float4 v = v4[n];
+    st[o] = v.x; st[o + nstride] = v.y; st[o + 2 * nstride] = v.z;
+}
+int vec_st_to_v4(tob_ctx_impl* c, const LevelGrid& g, const double* st, float4* v4) {
+    const long long n = (long long)g.nxn * g.nyn * g.nzl();
+    k_st_to_v4<<<div_up(n, 256), 256, 0, c->stream>>>(st, v4, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+int vec_v4_to_st(tob_ctx_impl* c, const LevelGrid& g, const float4* v4, double* st) {
+    const long long n = (long long)g.nxn * g.nyn * g.nzl();
+    k_v4_to_st<<<div_up(n, 256), 256, 0, c->stream>>>(v4, st, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride, g.zl_own0(), g.zl_own1());
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+// operand blocks of KE for the 8 shifts x 4 K-steps: B[(s*4+st)][chunk a'][row n (16)][4] = KE[3 ref(s) + n][3 ref(a',b',g') + c']
+int tc2_build_B(const Hex8Operator& op, float** dB) {
+    if (*dB) return 0;
+    auto ref = [](int a, int b, int g) { return (g ? 4 : 0) + (b ? (a ? 2 : 3) : (a ? 1 : 0)); };
+    std::vector<float> B(32 * 2 * 16 * 4, 0.0f);
+    for (int s = 0; s < 8; s++)
+        for (int st = 0; st < 4; st++)
+            for (int ap = 0; ap < 2; ap++)
+                for (int n = 0; n < 3; n++)
+                    for (int cp = 0; cp < 3; cp++) {
+                        const int row = 3 * ref(s & 1, (s >> 1) & 1, s >> 2) + n;
+                        const int col = 3 * ref(ap, st & 1, st >> 1) + cp;
+                        B[(size_t)(((s * 4 + st) * 2 + ap) * 16 + n) * 4 + cp] = (float)op.KE[row * 24 + col];
+                    }
+    TOB_CUDA(cudaMalloc(dB, sizeof(float) * B.size()));
+    TOB_CUDA(cudaMemcpy(*dB, B.data(), sizeof(float) * B.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// y4 = A x4 (epi 0) or one Chebyshev step (epi 1) on V4 vectors (ghost planes of x4 current, fixed dofs of x4 zero on entry of epi 0
+// is NOT required: fixed dofs are passed through, but they must not feed the products, so the caller keeps them zero)
+int hex8_tc32b(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float4* x4, float4* y4, const float* E32, const unsigned char* mask,
+               int epi, const float4* b4, const float4* dinv4, float4* d4, float s0, float s1) {
+    CUtensorMap tmX;
+    {
+        cuuint64_t dims[4] = {4, (cuuint64_t)g.nxn, (cuuint64_t)g.nyn, (cuuint64_t)g.nzl()};
+        cuuint64_t str[3] = {16, (cuuint64_t)g.nxn * 16, (cuuint64_t)g.nxn * g.nyn * 16};
+        cuuint32_t box[4] = {4, T2_PX, T2_PY, 1};
+        TOB_CHECK(encode_map(c, &tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x4, dims, str, box));
+    }
+    Tc2Params P;
+    P.y = y4; P.E32 = E32; P.mask = mask; P.B = dB; P.b = b4; P.dinv = dinv4; P.d = d4; P.s0 = s0; P.s1 = s1;
+    P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.pe = g.pe; P.pm = g.pm; P.estride = g.estride; P.mstride = g.mstride;
+    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi;
+    const int gx = div_up(g.nxn, T2_X), gy = div_up(g.nyn, T2_Y);
+    const int nz = P.zout1 - P.zout0;
+    int nch = std::max(1, std::min(nz / 8, (int)((4LL * c->num_sms * 2) / std::max(1, gx * gy))));
+    P.zchunk = div_up(nz, nch);
+    nch = div_up(nz, P.zchunk);
+    const int smem_bytes = T2_B_BYTES + 4 * T2_SLOT;
+    static bool attr_set[64] = {};
+    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
+        TOB_CUDA(cudaFuncSetAttribute(k_hex8_tc32b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
+    }
+    k_hex8_tc32b<<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
 }  // namespace tob
