@@ -425,13 +425,14 @@ def test_galerkin_coarse_operators_match_ptap(oracle, monkeypatch):
 @pytest.mark.parametrize("shape,xc", [((9, 5, 5), (0, 2, 0, 1, 0, 1)), ((34, 21, 13), (0, 2, 0, 1, 0, 1)), ((65, 33, 33), (0, 2, 0, 1, 0, 1)),
                                       ((20, 12, 9), (0, 1.3, 0, 0.7, 0, 0.45))])
 @pytest.mark.parametrize("dens", ["uniform", "random", "checker"])
-@pytest.mark.parametrize("gen", [1, 2])
+@pytest.mark.parametrize("gen", [1, 2, 3])
 def test_spmv_tf32_tensor_core_operator(oracle, shape, xc, dens, gen, monkeypatch):
     """The single-precision tensor-core operator (hex8_tc32.cu: tcgen05.mma kind::tf32, fp32 accumulation in TMEM) applies
     the same operator as the fp64 kernel up to TF32 input rounding (10-bit mantissa): <= 2e-3 of max|y| against the oracle;
     fixed dofs are passed through exactly (to fp32)."""
     from topopt_in_petsc_b200 import Context, LinearElasticity
-    # gen 1: element-row GEMM with gather / shared-memory scatter; gen 2: the tensor core reads the nodal planes directly
+    # gen 1: element-row GEMM with gather / shared-memory scatter; gen 2: the tensor core reads the nodal planes directly,
+    # one skinny product per element position; gen 3: the same operand view with element rows (wide tiles) + transposed node sums
     monkeypatch.setenv("TOB_TC32_GEN", str(gen))
     rng = np.random.default_rng(77)
     g = oracle.Grid(*shape, xc=xc)

@@ -534,7 +534,7 @@ void elast_destroy(tob_elast_impl* h) {
     for (auto e : h->prof_ev) cudaEventDestroy(e);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     sr_destroy(h);
-    cudaFree(h->u32); cudaFree(h->y32); cudaFree(h->keT32); cudaFree(h->x4); cudaFree(h->y4); cudaFree(h->E32); cudaFree(h->tcB);
+    cudaFree(h->u32); cudaFree(h->y32); cudaFree(h->keT32); cudaFree(h->x4); cudaFree(h->y4); cudaFree(h->E32); cudaFree(h->tcB); cudaFree(h->tcB3);
     cudaFree(h->mask);
     hex8_free_operator(h->op);
     delete h;
@@ -632,6 +632,7 @@ int tob::tc2_prepare(tob_elast_impl* h) {
         TOB_CUDA(cudaMemsetAsync(h->y4, 0, sizeof(float4) * nn, h->c->stream));
         TOB_CUDA(cudaMalloc(&h->E32, sizeof(float) * g.evec));
         TOB_CHECK(tc2_build_B(h->op, &h->tcB));
+        TOB_CHECK(tc3_build_B(h->op, &h->tcB3));
     }
     if (!h->E32_valid) {
         TOB_CHECK(vec_d2f(h->c, h->E_st, h->E32, g.evec));
@@ -655,7 +656,7 @@ int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
     TOB_CHECK(vec_zero(c, h->P, g.nvec));
     TOB_CHECK(nat_to_stored_dof(c, g, (const double*)du, h->P));
     TOB_CHECK(halo_nodes(c, g, h->P));
-    const int gen = getenv("TOB_TC32_GEN") ? atoi(getenv("TOB_TC32_GEN")) : 2;
+    const int gen = getenv("TOB_TC32_GEN") ? atoi(getenv("TOB_TC32_GEN")) : 3;
     if (gen == 1) {
         TOB_CHECK(vec_d2f(c, h->P, h->u32, g.nvec));
         TOB_CHECK(hex8_spmv_tc32(c, g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32));
@@ -665,7 +666,8 @@ int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
         TOB_CHECK(tc2_prepare(h));
         TOB_CHECK(vec_pointwise_mult(c, h->Z, h->P, h->NFREE, g.nvec));
         TOB_CHECK(vec_st_to_v4(c, g, h->Z, h->x4));
-        TOB_CHECK(hex8_tc32b(c, g, h->tcB, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f));
+        if (gen == 2) TOB_CHECK(hex8_tc32b(c, g, h->tcB, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f));
+        else TOB_CHECK(hex8_tc32c(c, g, h->tcB3, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f));
         TOB_CHECK(vec_v4_to_st(c, g, h->y4, h->Q));
         TOB_CHECK(vec_restore_fixed(c, h->Q + g.own_off, h->P + g.own_off, h->NFREE + g.own_off, g.own_len));
     }
@@ -676,13 +678,14 @@ int tob_elast_spmv_tf32(tob_elast* hh, const double* u, double* y) {
 int tob_elast_spmv_tf32_bench(tob_elast* hh, int reps, double* ms_per_apply) {
     auto* h = reinterpret_cast<tob_elast_impl*>(hh);
     tob_ctx_impl* c = h->c;
-    const int gen = getenv("TOB_TC32_GEN") ? atoi(getenv("TOB_TC32_GEN")) : 2;
+    const int gen = getenv("TOB_TC32_GEN") ? atoi(getenv("TOB_TC32_GEN")) : 3;
     if (!h->have_density || (gen == 1 ? !h->u32 : !h->x4)) TOB_FAIL("call tob_elast_spmv_tf32 once first");
     const size_t flush_bytes = 512ull << 20;
     TOB_CHECK(c->stage[7].reserve(flush_bytes));
     auto apply = [&]() -> int {
         if (gen == 1) return hex8_spmv_tc32(c, *h->g, h->op, h->u32, h->y32, h->E_st, h->mask, &h->keT32);
-        return hex8_tc32b(c, *h->g, h->tcB, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f);
+        if (gen == 2) return hex8_tc32b(c, *h->g, h->tcB, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f);
+        return hex8_tc32c(c, *h->g, h->tcB3, h->x4, h->y4, h->E32, h->mask, 0, nullptr, nullptr, nullptr, 0.f, 0.f);
     };
     for (int i = 0; i < 3; i++) TOB_CHECK(apply());
     cudaEvent_t e0, e1;

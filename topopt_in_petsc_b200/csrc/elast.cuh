@@ -39,7 +39,7 @@ struct tob_elast_impl {
     // fp32 scratch of the tensor-core operator (hex8_tc32.cu)
     float *u32 = nullptr, *y32 = nullptr, *keT32 = nullptr;
     float4 *x4 = nullptr, *y4 = nullptr;
-    float *E32 = nullptr, *tcB = nullptr;
+    float *E32 = nullptr, *tcB = nullptr, *tcB3 = nullptr;
     bool E32_valid = false;
     // single-reduction Jacobi-PCG (cgsr.cuh): u = D^-1 r lives in a peer-mapped buffer (the neighbours store its ghost planes)
     PeerVec sr_u;

@@ -232,7 +232,10 @@ static int cheb_smooth_tf32(tob_elast_impl* h, GmgLevel& L, int k, bool zero_ini
             TOB_KERNEL_CHECK();
             continue;
         }
-        TOB_CHECK(hex8_tc32b(c, g, h->tcB, xin, xout, h->E32, L.mask, 1, mg->b4, mg->dinv4, mg->d4, (float)s0, (float)s1));
+        if (getenv("TOB_TC32_GEN") && atoi(getenv("TOB_TC32_GEN")) == 2)
+            TOB_CHECK(hex8_tc32b(c, g, h->tcB, xin, xout, h->E32, L.mask, 1, mg->b4, mg->dinv4, mg->d4, (float)s0, (float)s1));
+        else
+            TOB_CHECK(hex8_tc32c(c, g, h->tcB3, xin, xout, h->E32, L.mask, 1, mg->b4, mg->dinv4, mg->d4, (float)s0, (float)s1));
         float4* t = xin; xin = xout; xout = t;
     }
     return vec_v4_to_st(c, g, xin, L.x);
@@ -446,6 +449,10 @@ int gmg_update(tob_elast_impl* h) {
     mg->lv[0].E = h->E_st;
     mg->lv[0].dinv = h->DINV;
     mg->lv[0].mask = h->mask;
+    if (mg->tf32) {  // the V-cycle is replayed as a CUDA graph: the fp32 copy of the modulus must be refreshed HERE, not inside it
+        h->E32_valid = false;
+        TOB_CHECK(tc2_prepare(h));
+    }
     for (size_t l = 1; l < mg->lv.size(); l++) {
         GmgLevel &F = mg->lv[l - 1], &C = mg->lv[l];
         const LevelGrid &f = F.g, &g = C.g;

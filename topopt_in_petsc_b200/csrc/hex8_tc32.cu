@@ -277,11 +277,16 @@ struct Tc2Params {
     int epi;
 };
 
+// PACKED: the eight accumulators share one 64-column TMEM window (D_s at column 4 s; the first MMA of a plane is an N = 32
+// tile that also clears the window, every other MMA accumulates -- rows 3..15 of the operand blocks are zero, so they add
+// nothing to their neighbours' columns) and the epilogue needs ONE tcgen05.ld instead of eight; 64 instead of 128 columns
+// also doubles the CTAs an SM can hold.
+template <bool PACKED>
 __global__ void __launch_bounds__(128)
 k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;                    // operand blocks of KE
-    unsigned char* sP = smem + T2_B_BYTES;       // 4 plane slots
+    unsigned char* sP = smem + T2_B_BYTES + 1024;  // 4 plane slots (after the N = 32 clearing block)
     __shared__ __align__(8) uint64_t full[4];
     __shared__ __align__(8) uint64_t mma_done;
     __shared__ uint32_t tmem_base_s;
@@ -292,14 +297,14 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
     const int z0 = P.zout0 + blockIdx.z * P.zchunk, z1 = min(z0 + P.zchunk, P.zout1);
     if (z0 >= z1) return;
 
-    for (int idx = t; idx < T2_B_BYTES / 16; idx += 128) reinterpret_cast<float4*>(sB)[idx] = reinterpret_cast<const float4*>(P.B)[idx];
+    for (int idx = t; idx < (T2_B_BYTES + 1024) / 16; idx += 128) reinterpret_cast<float4*>(sB)[idx] = reinterpret_cast<const float4*>(P.B)[idx];
     if (t == 0) {
         for (int s = 0; s < 4; s++) mbar_init(&full[s], 1);
         mbar_init(&mma_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(PACKED ? 64 : 128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // sB was written through the generic proxy
@@ -309,6 +314,7 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
     const uint32_t tmem = tmem_base_s;
     // D = F32, A = B = TF32, K-major both, N = 16, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (2u << 17) | (8u << 24);
+    const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // N = 32
     const uint32_t sB_addr = smem_u32(sB), sP_addr = smem_u32(sP);
 
     auto issue_plane = [&](int pz) {  // TMA: plane pz of this tile (with halo) -> slot pz & 3 (outside the grid: zeros)
@@ -345,12 +351,15 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
                     const int pz = z - g + gp;
                     const uint32_t aaddr = sP_addr + (uint32_t)((pz & 3) * T2_SLOT + ((1 - b + bp) * T2_PX + (1 - a)) * 16);
                     const uint64_t da = tc_smem_desc(aaddr, 16, T2_PX * 16);
-                    const uint64_t db = tc_smem_desc(sB_addr + (uint32_t)((s * 4 + st) * 512), 256, 128);
-                    const uint32_t acc = st > 0;
+                    const bool first = PACKED && s == 0 && st == 0;  // N = 32 block (rows 3..31 zero): writes D_0 and clears the window
+                    const uint64_t db = first ? tc_smem_desc(sB_addr + (uint32_t)T2_B_BYTES, 512, 128)
+                                              : tc_smem_desc(sB_addr + (uint32_t)((s * 4 + st) * 512), 256, 128);
+                    const uint32_t acc = PACKED ? (first ? 0u : 1u) : (uint32_t)(st > 0);
+                    const uint32_t id = first ? idesc32 : idesc;
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem + (uint32_t)(16 * s)), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                        ::"r"(tmem + (uint32_t)((PACKED ? 4 : 16) * s)), "l"(da), "l"(db), "r"(id), "r"(acc) : "memory");
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done)) : "memory");
@@ -367,17 +376,39 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         mbar_wait(&full[z & 3], (uint32_t)(((z - (z0 - 1)) >> 2) & 1));  // (already complete: makes the TMA writes of plane z visible to me)
         xo = *reinterpret_cast<const float4*>(sP + (z & 3) * T2_SLOT + ((iy + 1) * T2_PX + ix + 1) * 16);
         float acc[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-        for (int s = 0; s < 8; s++) {
-            uint32_t r0, r1, r2, r3;
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(16 * s);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+        if (PACKED) {
+            uint32_t d[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+                  "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
+                  "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
+                  "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+                : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const float Es = (s >> 2) ? Elo[s & 3] : Ehi[s & 3];
-            acc[0] = fmaf(Es, __uint_as_float(r0), acc[0]);
-            acc[1] = fmaf(Es, __uint_as_float(r1), acc[1]);
-            acc[2] = fmaf(Es, __uint_as_float(r2), acc[2]);
-            (void)r3;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const float Es = (s >> 2) ? Elo[s & 3] : Ehi[s & 3];
+                acc[0] = fmaf(Es, __uint_as_float(d[4 * s]), acc[0]);
+                acc[1] = fmaf(Es, __uint_as_float(d[4 * s + 1]), acc[1]);
+                acc[2] = fmaf(Es, __uint_as_float(d[4 * s + 2]), acc[2]);
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                uint32_t r0, r1, r2, r3;
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(16 * s);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float Es = (s >> 2) ? Elo[s & 3] : Ehi[s & 3];
+                acc[0] = fmaf(Es, __uint_as_float(r0), acc[0]);
+                acc[1] = fmaf(Es, __uint_as_float(r1), acc[1]);
+                acc[2] = fmaf(Es, __uint_as_float(r2), acc[2]);
+                (void)r3;
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (gi < P.nxn && gj < P.nyn) {
@@ -403,7 +434,7 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         __syncthreads();  // every thread is done with TMEM and with the tile of plane z - 1: recycle its slot
         if (t == 0 && z + 3 <= z1) issue_plane(z + 3);
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(PACKED ? 64 : 128) : "memory");
 }
 
 // ---- V4 (node-interleaved fp32) <-> stored fp64 layout ----------------------------------------------------------------------
@@ -444,7 +475,7 @@ int vec_v4_to_st(tob_ctx_impl* c, const LevelGrid& g, const float4* v4, double* 
 int tc2_build_B(const Hex8Operator& op, float** dB) {
     if (*dB) return 0;
     auto ref = [](int a, int b, int g) { return (g ? 4 : 0) + (b ? (a ? 2 : 3) : (a ? 1 : 0)); };
-    std::vector<float> B(32 * 2 * 16 * 4, 0.0f);
+    std::vector<float> B(32 * 2 * 16 * 4 + 256, 0.0f);  // + the N = 32 clearing block of (s, st) = (0, 0): [chunk 2][32 rows][4]
     for (int s = 0; s < 8; s++)
         for (int st = 0; st < 4; st++)
             for (int ap = 0; ap < 2; ap++)
@@ -454,6 +485,10 @@ int tc2_build_B(const Hex8Operator& op, float** dB) {
                         const int col = 3 * ref(ap, st & 1, st >> 1) + cp;
                         B[(size_t)(((s * 4 + st) * 2 + ap) * 16 + n) * 4 + cp] = (float)op.KE[row * 24 + col];
                     }
+    for (int ap = 0; ap < 2; ap++)
+        for (int n = 0; n < 3; n++)
+            for (int cp = 0; cp < 3; cp++)
+                B[(size_t)32 * 2 * 16 * 4 + (size_t)(ap * 32 + n) * 4 + cp] = (float)op.KE[(3 * ref(0, 0, 0) + n) * 24 + 3 * ref(ap, 0, 0) + cp];
     TOB_CUDA(cudaMalloc(dB, sizeof(float) * B.size()));
     TOB_CUDA(cudaMemcpy(*dB, B.data(), sizeof(float) * B.size(), cudaMemcpyHostToDevice));
     return 0;
@@ -476,16 +511,211 @@ int hex8_tc32b(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi;
     const int gx = div_up(g.nxn, T2_X), gy = div_up(g.nyn, T2_Y);
     const int nz = P.zout1 - P.zout0;
-    int nch = std::max(1, std::min(nz / 8, (int)((4LL * c->num_sms * 2) / std::max(1, gx * gy))));
+    int nch = std::max(1, std::min(nz / 8, (int)((6LL * c->num_sms * 2) / std::max(1, gx * gy))));
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
-    const int smem_bytes = T2_B_BYTES + 4 * T2_SLOT;
-    static bool attr_set[64] = {};
-    if (c->device < 0 || c->device >= 64 || !attr_set[c->device]) {
-        TOB_CUDA(cudaFuncSetAttribute(k_hex8_tc32b, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        if (c->device >= 0 && c->device < 64) attr_set[c->device] = true;
+    const int smem_bytes = T2_B_BYTES + 1024 + 4 * T2_SLOT;
+    static const bool packed = !(getenv("TOB_TC32_PACKED") && atoi(getenv("TOB_TC32_PACKED")) == 0);
+    if (packed) k_hex8_tc32b<true><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    else k_hex8_tc32b<false><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    c->launches++;
+    TOB_KERNEL_CHECK();
+    return 0;
+}
+
+
+// =========================================================================================================================
+// Generation 3: wide tiles.  ncu on generation 2 (profiles/r02_ncu_tc32b_256.txt): the tensor pipe is busy 79 % of the time --
+// an M128 x K8 tcgen05.mma costs ~33 cycles however narrow N is, and the per-shift products are N = 3.  Here the rows are
+// ELEMENTS (the window with lower corner node I), so one tile computes all 24 outputs of the element at once:
+//     D[e][0..23] = KE * u_e            4 MMAs of M 128, N 32, K 8 per 128 elements  (instead of 32 of N 16)
+// still without any gather (the A operand is the overlapping-descriptor view of the raw nodal planes).  What comes back is
+// per ELEMENT, so the epilogue scales the row by the element's modulus and sums the eight element contributions of a node
+// through a transposed shared-memory buffer (24 conflict-free stores per element thread, 24 conflict-free loads per node
+// thread, no atomics); contributions to the plane above are carried in registers to the next layer.  Tiles overlap by one
+// element (7 x 15 complete nodes per 8 x 16 elements).  The MMAs of layer L + 1 are issued before the node sums of layer L,
+// so the tensor pipe works under the epilogue.
+// =========================================================================================================================
+constexpr int T3_EX = 8, T3_EY = 16;               // elements per tile layer (= UMMA M)
+constexpr int T3_PX = T3_EX + 1, T3_PY = T3_EY + 1;
+constexpr int T3_SLOT = ((T3_PX * T3_PY * 16 + 127) / 128) * 128;
+constexpr int T3_B_BYTES = 4 * 1024;               // 4 K-steps x (2 chunks x 32 rows x 16 B)
+constexpr int T3_Y_BYTES = 24 * 128 * 4;           // one transposed output buffer
+
+__global__ void __launch_bounds__(128)
+k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc2Params P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;
+    unsigned char* sP = smem + T3_B_BYTES;                     // 4 plane slots
+    float* sY = reinterpret_cast<float*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // 2 x [24][128]
+    __shared__ __align__(8) uint64_t full[4];
+    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int ix = t & (T3_EX - 1), iy = t >> 3;
+    const int oi = blockIdx.x * (T3_EX - 1) - 1, oj = blockIdx.y * (T3_EY - 1) - 1;  // node index of the tile origin
+    const int gi = oi + ix, gj = oj + iy;  // my element (lower-corner node) = my node
+    const int z0 = P.zout0 + blockIdx.z * P.zchunk, z1 = min(z0 + P.zchunk, P.zout1);
+    if (z0 >= z1) return;
+
+    for (int idx = t; idx < T3_B_BYTES / 16; idx += 128) reinterpret_cast<float4*>(sB)[idx] = reinterpret_cast<const float4*>(P.B)[idx];
+    if (t == 0) {
+        for (int s = 0; s < 4; s++) mbar_init(&full[s], 1);
+        mbar_init(&mma_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    k_hex8_tc32b<<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (4u << 17) | (8u << 24);  // F32 += TF32 x TF32, N 32, M 128
+    const uint32_t sB_addr = smem_u32(sB), sP_addr = smem_u32(sP);
+    const int pfirst = z0 - 1;  // first plane / layer of the chunk
+
+    auto issue_plane = [&](int pz) {
+        const int s = pz & 3;
+        mbar_expect_tx(&full[s], T3_PX * T3_PY * 16);
+        tma_load_4d(sP + s * T3_SLOT, &tmX, &full[s], 0, oi, oj, pz);
+    };
+    auto wait_plane = [&](int pz) { mbar_wait(&full[pz & 3], (uint32_t)(((pz - pfirst) >> 2) & 1)); };
+    auto issue_mma = [&](int L) {  // layer L: planes L (g' = 0) and L + 1 (g' = 1)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int st = 0; st < 4; st++) {
+            const int bp = st & 1, gp = st >> 1;
+            const uint32_t aaddr = sP_addr + (uint32_t)(((L + gp) & 3) * T3_SLOT + bp * T3_PX * 16);
+            const uint64_t da = tc_smem_desc(aaddr, 16, T3_PX * 16);
+            const uint64_t db = tc_smem_desc(sB_addr + (uint32_t)(st * 1024), 512, 128);
+            const uint32_t acc = st > 0;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done)) : "memory");
+    };
+    if (t == 0) {
+        for (int pz = pfirst; pz <= pfirst + 3 && pz <= z1; pz++) issue_plane(pz);
+        wait_plane(pfirst);
+        wait_plane(pfirst + 1);
+        issue_mma(pfirst);
+    }
+    const bool elem_in = gi >= 0 && gi < P.nxn - 1 && gj >= 0 && gj < P.nyn - 1;
+    const bool node_out = ix >= 1 && iy >= 1 && gi < P.nxn && gj < P.nyn;
+    float carry[3] = {0.0f, 0.0f, 0.0f};
+    uint32_t mphase = 0;
+    for (int L = pfirst; L < z1; L++) {
+        const float Ee = (elem_in && L >= 0 && L < P.nzl - 1) ? P.E32[(long long)L * P.estride + (long long)gj * P.pe + gi] : 0.0f;
+        mbar_wait(&mma_done, mphase);
+        mphase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* Yb = sY + (L & 1) * (24 * 128);
+        {
+            uint32_t d[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]), "=r"(d[9]),
+                  "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15]), "=r"(d[16]), "=r"(d[17]), "=r"(d[18]),
+                  "=r"(d[19]), "=r"(d[20]), "=r"(d[21]), "=r"(d[22]), "=r"(d[23]), "=r"(d[24]), "=r"(d[25]), "=r"(d[26]), "=r"(d[27]),
+                  "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 24; k++) Yb[k * 128 + t] = Ee * __uint_as_float(d[k]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // Yb complete; TMEM free; everybody is past the epilogue of layer L - 1 (slot of plane L - 1 free)
+        if (t == 0 && L + 1 < z1) {
+            if (L + 3 <= z1 && L + 3 > pfirst + 3) issue_plane(L + 3);
+            wait_plane(L + 2);  // (plane L + 1 was waited for before the previous MMA)
+            issue_mma(L + 1);
+        }
+        // ---- node sums: plane L gets `carry` (from layer L - 1) + the lower-node outputs of layer L -------------------------------
+        float low[3] = {0.0f, 0.0f, 0.0f}, up[3] = {0.0f, 0.0f, 0.0f};
+        if (ix >= 1 && iy >= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int a = q & 1, b = q >> 1;
+                const int e = t - (8 * b + a);
+                const int nlo = b ? (a ? 2 : 3) : (a ? 1 : 0);  // reference local node (a, b, 0); (a, b, 1) = nlo + 4
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    low[c] += Yb[(3 * nlo + c) * 128 + e];
+                    up[c] += Yb[(3 * (nlo + 4) + c) * 128 + e];
+                }
+            }
+        }
+        if (L >= z0 && node_out) {
+            wait_plane(L);  // (complete long ago: orders my generic read of the TMA-written tile)
+            const float4 xo = *reinterpret_cast<const float4*>(sP + (L & 3) * T3_SLOT + (iy * T3_PX + ix) * 16);
+            const unsigned char m = P.mask[(long long)L * P.mstride + (long long)gj * P.pm + gi];
+            const float xs[3] = {xo.x, xo.y, xo.z};
+            float au[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) au[c] = ((m >> c) & 1) ? xs[c] : carry[c] + low[c];
+            const long long o = ((long long)L * P.nyn + gj) * P.nxn + gi;
+            if (P.epi == 0) {
+                P.y[o] = make_float4(au[0], au[1], au[2], 0.0f);
+            } else {
+                const float4 bv = P.b[o], dv = P.dinv[o], dd = P.d[o];
+                const float d0 = P.s0 * dd.x + P.s1 * dv.x * (bv.x - au[0]);
+                const float d1 = P.s0 * dd.y + P.s1 * dv.y * (bv.y - au[1]);
+                const float d2 = P.s0 * dd.z + P.s1 * dv.z * (bv.z - au[2]);
+                P.d[o] = make_float4(d0, d1, d2, 0.0f);
+                P.y[o] = make_float4(xo.x + d0, xo.y + d1, xo.z + d2, 0.0f);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) carry[c] = up[c];
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32) : "memory");
+}
+
+// operand blocks for generation 3: B[step (b', g')][chunk a'][row n (32)][4] = KE[n][3 ref(a', b', g') + c']
+int tc3_build_B(const Hex8Operator& op, float** dB) {
+    if (*dB) return 0;
+    auto ref = [](int a, int b, int g) { return (g ? 4 : 0) + (b ? (a ? 2 : 3) : (a ? 1 : 0)); };
+    std::vector<float> B(4 * 2 * 32 * 4, 0.0f);
+    for (int st = 0; st < 4; st++)
+        for (int ap = 0; ap < 2; ap++)
+            for (int n = 0; n < 24; n++)
+                for (int cp = 0; cp < 3; cp++)
+                    B[(size_t)((st * 2 + ap) * 32 + n) * 4 + cp] = (float)op.KE[n * 24 + 3 * ref(ap, st & 1, st >> 1) + cp];
+    TOB_CUDA(cudaMalloc(dB, sizeof(float) * B.size()));
+    TOB_CUDA(cudaMemcpy(*dB, B.data(), sizeof(float) * B.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float4* x4, float4* y4, const float* E32, const unsigned char* mask,
+               int epi, const float4* b4, const float4* dinv4, float4* d4, float s0, float s1) {
+    CUtensorMap tmX;
+    {
+        cuuint64_t dims[4] = {4, (cuuint64_t)g.nxn, (cuuint64_t)g.nyn, (cuuint64_t)g.nzl()};
+        cuuint64_t str[3] = {16, (cuuint64_t)g.nxn * 16, (cuuint64_t)g.nxn * g.nyn * 16};
+        cuuint32_t box[4] = {4, T3_PX, T3_PY, 1};
+        TOB_CHECK(encode_map(c, &tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x4, dims, str, box));
+    }
+    Tc2Params P;
+    P.y = y4; P.E32 = E32; P.mask = mask; P.B = dB; P.b = b4; P.dinv = dinv4; P.d = d4; P.s0 = s0; P.s1 = s1;
+    P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.pe = g.pe; P.pm = g.pm; P.estride = g.estride; P.mstride = g.mstride;
+    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi;
+    const int gx = div_up(g.nxn, T3_EX - 1), gy = div_up(g.nyn, T3_EY - 1);
+    const int nz = P.zout1 - P.zout0;
+    int nch = std::max(1, std::min(nz / 8, (int)((5LL * c->num_sms * 2) / std::max(1, gx * gy))));
+    P.zchunk = div_up(nz, nch);
+    nch = div_up(nz, P.zchunk);
+    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + 2 * T3_Y_BYTES;
+    k_hex8_tc32c<<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;
