@@ -85,6 +85,7 @@ int elast_set_density(tob_elast_impl* h, const double* xphys_nat_dev, double Emi
     TOB_CHECK(halo_elems(c, h->xphys_st, g.estride, own0, own1, 0, recv_hi, send_down, 0));
     TOB_CHECK(simp_modulus(c, h->xphys_st, h->E_st, g.evec, Emin, Emax, penal));
     TOB_CHECK(hex8_diag_inv(c, g, h->op, h->E_st, h->mask, h->DINV, true));
+    TOB_CHECK(vec_d2f(c, h->DINV, h->DINV32, g.nvec));
     h->Emin = Emin; h->Emax = Emax; h->penal = penal;
     h->have_density = true;
     h->E32_valid = false;
@@ -243,14 +244,14 @@ int elast_pcg(tob_elast_impl* h) {
         double* blk_cur = c->d_partials + (256 << 10);
         double* blk_nxt = c->d_partials + (512 << 10);
         int nbx = 0;
-        TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->R, h->R, h->DINV, nullptr, 0, nullptr, blk_cur, &nbx));
-        TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV, nullptr, nullptr));
+        TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->R, h->R, h->DINV32, nullptr, 0, nullptr, blk_cur, &nbx));
+        TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, nullptr, nullptr));
         const int check = o.check_every > 0 ? o.check_every : 10;
         const bool graphed1 = !getenv("TOB_PCG_NOGRAPH") && check >= 4;
         auto one_iteration1 = [&](double* bc, double* bn) -> int {
             TOB_CHECK(elast_apply(h, h->P, h->Q, EPI_DOT, false, 0, nullptr, &np));
-            TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV, c->d_partials, np, bc, bn, &nbx));
-            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV, bn, bc));
+            TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV32, c->d_partials, np, bc, bn, &nbx));
+            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, bn, bc));
             return 0;
         };
         const int stride_saved1 = h->prof_stride;
@@ -295,7 +296,7 @@ int elast_pcg(tob_elast_impl* h) {
         h->prof_stride = stride_saved1;
         while (!graphed1 && it < o.maxits) {
             TOB_CHECK(elast_apply(h, h->P, h->Q, EPI_DOT, false, 0, nullptr, &np));
-            TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV, c->d_partials, np, blk_cur, blk_nxt, &nbx));
+            TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV32, c->d_partials, np, blk_cur, blk_nxt, &nbx));
             it++;
             if (it % check == 0 || it == o.maxits) {
                 TOB_CHECK(finalize_parts(c, blk_nxt, nbx, S_TMP));
@@ -304,7 +305,7 @@ int elast_pcg(tob_elast_impl* h) {
                 if (!(rnorm == rnorm)) TOB_FAIL("PCG produced NaN (bad density field)");
                 if (rnorm <= tol || rnorm > o.dtol * bnorm) break;
             }
-            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV, blk_nxt, blk_cur));
+            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, blk_nxt, blk_cur));
             double* t = blk_cur; blk_cur = blk_nxt; blk_nxt = t;
         }
     } else if (rnorm > tol && bnorm > 0) {
@@ -464,7 +465,10 @@ int elast_set_bc_load(tob_elast_impl* h, const unsigned char* fixed, const doubl
     double bb = 0;
     TOB_CHECK(read_scalars(c, S_BB, 1, &bb));
     h->bnorm = sqrt(bb);
-    if (h->have_density) TOB_CHECK(hex8_diag_inv(c, g, h->op, h->E_st, h->mask, h->DINV, true));
+    if (h->have_density) {
+        TOB_CHECK(hex8_diag_inv(c, g, h->op, h->E_st, h->mask, h->DINV, true));
+        TOB_CHECK(vec_d2f(c, h->DINV, h->DINV32, g.nvec));
+    }
     if (h->mg) {
         TOB_CHECK(gmg_refresh_masks(h));
         if (h->have_density) TOB_CHECK(gmg_update(h));
@@ -513,6 +517,8 @@ int elast_create(tob_ctx_impl* c, double nu, const tob_solver_opts* opts, tob_el
     TOB_CHECK(alloc_vec(c, &h->xphys_st, g.evec));
     TOB_CHECK(alloc_vec(c, &h->E_st, g.evec));
     TOB_CUDA(cudaMalloc(&h->mask, (size_t)g.mstride * g.nzl()));
+    TOB_CUDA(cudaMalloc(&h->DINV32, sizeof(float) * g.nvec));
+    TOB_CUDA(cudaMemsetAsync(h->DINV32, 0, sizeof(float) * g.nvec, c->stream));
     TOB_CHECK(alloc_vec(c, &h->nat_dof, 3 * g.owned_nodes()));
     TOB_CHECK(alloc_vec(c, &h->nat_dof2, 3 * g.owned_nodes()));
     TOB_CHECK(alloc_vec(c, &h->nat_el, g.owned_elems()));
@@ -534,6 +540,7 @@ void elast_destroy(tob_elast_impl* h) {
     for (auto e : h->prof_ev) cudaEventDestroy(e);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     sr_destroy(h);
+    cudaFree(h->DINV32);
     cudaFree(h->u32); cudaFree(h->y32); cudaFree(h->keT32); cudaFree(h->x4); cudaFree(h->y4); cudaFree(h->E32); cudaFree(h->tcB); cudaFree(h->tcB3);
     cudaFree(h->mask);
     hex8_free_operator(h->op);

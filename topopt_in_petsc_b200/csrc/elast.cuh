@@ -17,6 +17,7 @@ struct tob_elast_impl {
     // stored-layout nodal vectors
     double *U = nullptr, *B = nullptr, *RHS = nullptr, *R = nullptr, *P = nullptr, *Q = nullptr, *Z = nullptr;
     double *DINV = nullptr, *NFREE = nullptr;
+    float* DINV32 = nullptr;  // the Jacobi preconditioner of the one-rank PCG kernels, single precision (vecops.cu)
     unsigned char* mask = nullptr;
     // stored element fields
     double *xphys_st = nullptr, *E_st = nullptr;

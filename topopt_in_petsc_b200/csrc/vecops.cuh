@@ -17,9 +17,9 @@ int vec_pointwise_mult(tob_ctx_impl* c, double* y, const double* a, const double
 int vec_fill(tob_ctx_impl* c, double* y, double v, long long n);
 int vec_restore_fixed(tob_ctx_impl* c, double* y, const double* u, const double* nf, long long n);
 // single-rank Jacobi-PCG kernels that consume per-CTA partial sums directly (no finalize launches)
-int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const double* dinv,
+int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const float* dinv,
                     const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out);
-int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const double* dinv, const double* new_parts,
+int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const float* dinv, const double* new_parts,
                    const double* old_parts);
 int finalize_parts(tob_ctx_impl* c, const double* parts, int nb, int slot);
 }  // namespace tob
