@@ -22,7 +22,8 @@ def test_hs_golden(shape, rmin, key):
 
 
 @pytest.mark.parametrize("shape,xc,rmin", [((17, 9, 9), (0, 2, 0, 1, 0, 1), 0.3), ((21, 13, 11), (0, 2, 0, 1, 0, 1), 0.25),
-                                           ((13, 9, 7), (0, 1.0, 0, 0.9, 0, 0.5), 0.21), ((9, 5, 5), (0, 2, 0, 1, 0, 1), 5.0)])
+                                           ((13, 9, 7), (0, 1.0, 0, 0.9, 0, 0.5), 0.21), ((9, 5, 5), (0, 2, 0, 1, 0, 1), 5.0),
+                                           ((33, 17, 17), (0, 2, 0, 1, 0, 1), 0.2)])  # the last one: ElemConn 3 (7^3 box, tiled kernel <3>)
 @pytest.mark.parametrize("ftype", [0, 1, 3])
 @pytest.mark.parametrize("proj", [False, True])
 def test_filter_project_gradients(oracle, shape, xc, rmin, ftype, proj):

@@ -36,10 +36,11 @@ def test_generation3_element_rows(oracle):
     for st in range(4):  # K-step (b', g'); chunks a' = 0, 1
         bp, gp = st & 1, st >> 1
         A = umma_rows(smem, gp * slot + bp * PX * 16, 16, PX * 16)
-        B = np.zeros((32, 8), dtype=np.float32)  # tc3_build_B: B[n][a' * 4 + c'] = KE[n][3 ref(a', b', g') + c']
+        B = np.zeros((32, 8), dtype=np.float32)  # tc3_build_B: B[4 node + c][a' * 4 + c'] = KE[3 node + c][3 ref(a', b', g') + c']
         for ap in range(2):
-            for n in range(24):
-                B[n, 4 * ap:4 * ap + 3] = KE[n, 3 * ref(ap, bp, gp):3 * ref(ap, bp, gp) + 3]
+            for nd in range(8):
+                for c in range(3):
+                    B[4 * nd + c, 4 * ap:4 * ap + 3] = KE[3 * nd + c, 3 * ref(ap, bp, gp):3 * ref(ap, bp, gp) + 3]
         D += A.astype(np.float64) @ B.astype(np.float64).T
     for e in (0, 5, 8, 77, 127):
         ex, ey = e % 8, e // 8
@@ -48,7 +49,8 @@ def test_generation3_element_rows(oracle):
             for b in range(2):
                 for a in range(2):
                     ue[3 * ref(a, b, gg):3 * ref(a, b, gg) + 3] = planes[gg][ey + b, ex + a, :3]
-        assert np.abs(D[e, :24] - KE.astype(np.float64) @ ue).max() <= 1e-5
+        got = D[e].reshape(8, 4)
+        assert np.abs(got[:, :3].reshape(-1) - KE.astype(np.float64) @ ue).max() <= 1e-5 and np.abs(got[:, 3]).max() == 0.0
 
 
 def test_generation2_node_rows_with_shifts(oracle):

@@ -64,7 +64,7 @@ k_cone(const double* __restrict__ in, double* __restrict__ out, const double* __
     out[nidx] = v;
 }
 
-// ---- TMA-tiled cone filter (modes 0-2, s = 1 or 2) ------------------------------------------------------------
+// ---- TMA-tiled cone filter (modes 0-2, s = 1, 2 or 3) ------------------------------------------------------------
 // One CTA produces a 32 x 8 x CT_Z block of outputs.  A single TMA box load brings the block plus its s-wide rim
 // into shared memory; everything outside the stored field (domain boundary, pitch padding, layers beyond the ghost
 // range) is zero-filled by the TMA unit, which is exactly the clipped box of Filter.cc:417-419 for the weighted sum
@@ -194,6 +194,7 @@ static int cone_apply(tob_filter_impl* h, const double* in_st, double* out, cons
     if (mode != 3 && h->tiled) {
         if (h->s == 1) return cone_apply_tiled<1>(h, in_st, out, xnat, mode);
         if (h->s == 2) return cone_apply_tiled<2>(h, in_st, out, xnat, mode);
+        if (h->s == 3) return cone_apply_tiled<3>(h, in_st, out, xnat, mode);  // 7^3 box: 64 distinct weights in registers, 1 CTA per SM
     }
     if (mode == 3) { l0 = 0; l1 = h->nl; }
     dim3 grid(div_up(g.nex, 128), g.ney, l1 - l0);

@@ -14,6 +14,8 @@ struct StencilLevel {
     bool pv_init = false;
     double* Ainv = nullptr;  // coarsest level: explicit inverse (dense, ndense x ndense), refreshed with the operator
     int ndense = 0;
+    double* prow = nullptr;      // double-buffered pivot row of the inversion
+    unsigned int* bar = nullptr; // its grid-barrier counter
     double* M = nullptr;     // [8][24][24] Q_child^T KE Q_child (level assembled from a matrix-free parent)
 };
 

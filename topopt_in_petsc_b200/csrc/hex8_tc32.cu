@@ -540,16 +540,16 @@ constexpr int T3_EX = 8, T3_EY = 16;               // elements per tile layer (=
 constexpr int T3_PX = T3_EX + 1, T3_PY = T3_EY + 1;
 constexpr int T3_SLOT = ((T3_PX * T3_PY * 16 + 127) / 128) * 128;
 constexpr int T3_B_BYTES = 4 * 1024;               // 4 K-steps x (2 chunks x 32 rows x 16 B)
-constexpr int T3_Y_BYTES = 24 * 128 * 4;           // one transposed output buffer
+constexpr int T3_Y_BYTES = 8 * 128 * 16;           // one transposed output buffer: [local node (8)][element (128)] float4
 
 __global__ void __launch_bounds__(128)
 k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sP = smem + T3_B_BYTES;                     // 4 plane slots
-    float* sY = reinterpret_cast<float*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // 2 x [24][128]
+    float4* sY = reinterpret_cast<float4*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // 2 x [8][128]
     __shared__ __align__(8) uint64_t full[4];
-    __shared__ __align__(8) uint64_t mma_done;
+    __shared__ __align__(8) uint64_t mma_done[2];  // one per TMEM accumulator (the MMAs run one layer ahead of the epilogue)
     __shared__ uint32_t tmem_base_s;
 
     const int t = threadIdx.x, warp = t >> 5;
@@ -562,11 +562,12 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
     for (int idx = t; idx < T3_B_BYTES / 16; idx += 128) reinterpret_cast<float4*>(sB)[idx] = reinterpret_cast<const float4*>(P.B)[idx];
     if (t == 0) {
         for (int s = 0; s < 4; s++) mbar_init(&full[s], 1);
-        mbar_init(&mma_done, 1);
+        mbar_init(&mma_done[0], 1);
+        mbar_init(&mma_done[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(32) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(64) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -584,7 +585,8 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         tma_load_4d(sP + s * T3_SLOT, &tmX, &full[s], 0, oi, oj, pz);
     };
     auto wait_plane = [&](int pz) { mbar_wait(&full[pz & 3], (uint32_t)(((pz - pfirst) >> 2) & 1)); };
-    auto issue_mma = [&](int L) {  // layer L: planes L (g' = 0) and L + 1 (g' = 1)
+    auto issue_mma = [&](int L) {  // layer L: planes L (g' = 0) and L + 1 (g' = 1); accumulator (L - pfirst) & 1
+        const int buf = (L - pfirst) & 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int st = 0; st < 4; st++) {
@@ -596,9 +598,9 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                ::"r"(tmem + (uint32_t)(32 * buf)), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done)) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[buf])) : "memory");
     };
     if (t == 0) {
         for (int pz = pfirst; pz <= pfirst + 3 && pz <= z1; pz++) issue_plane(pz);
@@ -609,16 +611,19 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
     const bool elem_in = gi >= 0 && gi < P.nxn - 1 && gj >= 0 && gj < P.nyn - 1;
     const bool node_out = ix >= 1 && iy >= 1 && gi < P.nxn && gj < P.nyn;
     float carry[3] = {0.0f, 0.0f, 0.0f};
-    uint32_t mphase = 0;
     for (int L = pfirst; L < z1; L++) {
         const float Ee = (elem_in && L >= 0 && L < P.nzl - 1) ? P.E32[(long long)L * P.estride + (long long)gj * P.pe + gi] : 0.0f;
-        mbar_wait(&mma_done, mphase);
-        mphase ^= 1;
+        if (t == 0 && L + 1 < z1) {  // the tensor core works one layer ahead: its accumulator was read out an iteration ago
+            wait_plane(L + 2);       // (plane L + 1 was waited for before the previous MMA)
+            issue_mma(L + 1);
+        }
+        const int buf = (L - pfirst) & 1;
+        mbar_wait(&mma_done[buf], (uint32_t)(((L - pfirst) >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* Yb = sY + (L & 1) * (24 * 128);
+        float4* Yb = sY + (L & 1) * (8 * 128);
         {
             uint32_t d[32];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(32 * buf);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -630,15 +635,12 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < 24; k++) Yb[k * 128 + t] = Ee * __uint_as_float(d[k]);
+            for (int n = 0; n < 8; n++)  // D columns are laid out [local node][4] (the operand blocks pad every node to 4 rows)
+                Yb[n * 128 + t] = make_float4(Ee * __uint_as_float(d[4 * n]), Ee * __uint_as_float(d[4 * n + 1]), Ee * __uint_as_float(d[4 * n + 2]), 0.0f);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // Yb complete; TMEM free; everybody is past the epilogue of layer L - 1 (slot of plane L - 1 free)
-        if (t == 0 && L + 1 < z1) {
-            if (L + 3 <= z1 && L + 3 > pfirst + 3) issue_plane(L + 3);
-            wait_plane(L + 2);  // (plane L + 1 was waited for before the previous MMA)
-            issue_mma(L + 1);
-        }
+        if (t == 0 && L + 3 <= z1 && L + 3 > pfirst + 3) issue_plane(L + 3);
         // ---- node sums: plane L gets `carry` (from layer L - 1) + the lower-node outputs of layer L -------------------------------
         float low[3] = {0.0f, 0.0f, 0.0f}, up[3] = {0.0f, 0.0f, 0.0f};
         if (ix >= 1 && iy >= 1) {
@@ -647,11 +649,9 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
                 const int a = q & 1, b = q >> 1;
                 const int e = t - (8 * b + a);
                 const int nlo = b ? (a ? 2 : 3) : (a ? 1 : 0);  // reference local node (a, b, 0); (a, b, 1) = nlo + 4
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    low[c] += Yb[(3 * nlo + c) * 128 + e];
-                    up[c] += Yb[(3 * (nlo + 4) + c) * 128 + e];
-                }
+                const float4 vl = Yb[nlo * 128 + e], vu = Yb[(nlo + 4) * 128 + e];
+                low[0] += vl.x; low[1] += vl.y; low[2] += vl.z;
+                up[0] += vu.x; up[1] += vu.y; up[2] += vu.z;
             }
         }
         if (L >= z0 && node_out) {
@@ -678,19 +678,20 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         for (int c = 0; c < 3; c++) carry[c] = up[c];
     }
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
 }
 
-// operand blocks for generation 3: B[step (b', g')][chunk a'][row n (32)][4] = KE[n][3 ref(a', b', g') + c']
+// operand blocks for generation 3: B[step (b', g')][chunk a'][row 4 * node + c (32)][4] = KE[3 * node + c][3 ref(a', b', g') + c']
 int tc3_build_B(const Hex8Operator& op, float** dB) {
     if (*dB) return 0;
     auto ref = [](int a, int b, int g) { return (g ? 4 : 0) + (b ? (a ? 2 : 3) : (a ? 1 : 0)); };
     std::vector<float> B(4 * 2 * 32 * 4, 0.0f);
     for (int st = 0; st < 4; st++)
         for (int ap = 0; ap < 2; ap++)
-            for (int n = 0; n < 24; n++)
-                for (int cp = 0; cp < 3; cp++)
-                    B[(size_t)((st * 2 + ap) * 32 + n) * 4 + cp] = (float)op.KE[n * 24 + 3 * ref(ap, st & 1, st >> 1) + cp];
+            for (int nd = 0; nd < 8; nd++)      // output row 4 * node + c (c < 3; the fourth row of every node stays zero)
+                for (int c = 0; c < 3; c++)
+                    for (int cp = 0; cp < 3; cp++)
+                        B[(size_t)((st * 2 + ap) * 32 + 4 * nd + c) * 4 + cp] = (float)op.KE[(3 * nd + c) * 24 + 3 * ref(ap, st & 1, st >> 1) + cp];
     TOB_CUDA(cudaMalloc(dB, sizeof(float) * B.size()));
     TOB_CUDA(cudaMemcpy(*dB, B.data(), sizeof(float) * B.size(), cudaMemcpyHostToDevice));
     return 0;
