@@ -102,7 +102,18 @@ for shape2 in ((17, 9, 33), (17, 9, 29)):
     assert st2.rel_residual <= 1e-9
     if rank == 0:
         print("gmg", shape2, "iterations", st.iterations, st2.iterations, flush=True)
-    pmg.close(); ctx2.close()
+    pmg.close()
+    # the same solve with the finest-level smoother in single precision on the tensor cores (TF32; the interleaved fp32 iterate is
+    # halo-exchanged between the two slabs): same answer, about the same number of outer iterations
+    os.environ["TOB_GMG_TF32"] = "1"
+    ptf = LinearElasticity(ctx2, opts=solver_opts(pc=1, nlvls=3, rtol=1e-9, maxits=300))
+    stf = ptf.SolveState(x2[a0:a1].copy(), 1e-9, 1.0, 3.0)
+    os.environ["TOB_GMG_TF32"] = "0"
+    assert stf.rel_residual <= 1e-9 and stf.iterations <= st.iterations + 8, ("tf32 smoother", shape2, stf.iterations, st.iterations)
+    assert np.abs(ptf.GetStateField() - U2[b0:b1]).max() <= 1e-6 * np.abs(U2).max(), ("tf32 smoother state", shape2)
+    if rank == 0:
+        print("gmg + tf32 smoother", shape2, "iterations", stf.iterations, flush=True)
+    ptf.close(); ctx2.close()
 # MMA
 mo, mg = o.MMAOracle(g.nel, 1), MMA(ctx, 1)
 xm = np.full(g.nel, 0.3)

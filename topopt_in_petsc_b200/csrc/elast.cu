@@ -632,7 +632,7 @@ static int tc32_buffers(tob_elast_impl* h) {
 // buffers / operand blocks / fp32 modulus of the generation-2 tensor-core operator
 int tob::tc2_prepare(tob_elast_impl* h) {
     const LevelGrid& g = *h->g;
-    const long long nn = (long long)g.nxn * g.nyn * g.nzl();
+    const long long nn = v4_plane_nodes(g) * g.nzl();
     if (!h->x4) {
         TOB_CUDA(cudaMalloc(&h->x4, sizeof(float4) * nn));
         TOB_CUDA(cudaMalloc(&h->y4, sizeof(float4) * nn));

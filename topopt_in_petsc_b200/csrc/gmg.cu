@@ -203,8 +203,12 @@ static int cheb_smooth_tf32(tob_elast_impl* h, GmgLevel& L, int k, bool zero_ini
     tob_ctx_impl* c = h->c;
     GmgHierarchy* mg = h->mg;
     const LevelGrid& g = L.g;
-    const long long nn = (long long)g.nxn * g.nyn * g.nzl();
+    const long long nn = v4_plane_nodes(g) * g.nzl();
     TOB_CHECK(tc2_prepare(h));
+    // halo of a V4 vector: one plane = v4_plane_nodes float4 = 2 * v4_plane_nodes doubles (a multiple of 4) for the generic halo kernel
+    LevelGrid g4 = g;
+    g4.pstride = 2 * v4_plane_nodes(g);
+    g4.nvec = g4.pstride * g.nzl();
     if (!mg->xa4) {
         float4** vs[] = {&mg->xa4, &mg->xb4, &mg->b4, &mg->d4, &mg->dinv4};
         for (auto v : vs) {
@@ -232,6 +236,7 @@ static int cheb_smooth_tf32(tob_elast_impl* h, GmgLevel& L, int k, bool zero_ini
             TOB_KERNEL_CHECK();
             continue;
         }
+        TOB_CHECK(halo_nodes(c, g4, reinterpret_cast<double*>(xin)));  // no-op on one rank
         if (getenv("TOB_TC32_GEN") && atoi(getenv("TOB_TC32_GEN")) == 2)
             TOB_CHECK(hex8_tc32b(c, g, h->tcB, xin, xout, h->E32, L.mask, 1, mg->b4, mg->dinv4, mg->d4, (float)s0, (float)s1));
         else
@@ -517,9 +522,9 @@ int gmg_setup(tob_elast_impl* h) {
         dI = std::min(aligned, small);
     }
     mg->dI = dI;
-    // TOB_GMG_TF32=1: finest-level smoothing in single precision on the tensor cores (one rank; the halo of the interleaved
-    // fp32 vectors is not wired yet)
-    mg->tf32 = getenv("TOB_GMG_TF32") && atoi(getenv("TOB_GMG_TF32")) != 0 && nranks == 1;
+    // TOB_GMG_TF32=1: finest-level smoothing in single precision on the tensor cores (the interleaved fp32 iterate is halo-exchanged
+    // like any nodal vector: one plane = a whole number of 32-byte units)
+    mg->tf32 = getenv("TOB_GMG_TF32") && atoi(getenv("TOB_GMG_TF32")) != 0;
     const int ndist = dI >= 0 ? dI + 1 : nres;       // distributed levels (single rank: all of them)
     const int nl = dI >= 0 ? ndist + (nres - dI) : nres;
     mg->lv.resize(nl);

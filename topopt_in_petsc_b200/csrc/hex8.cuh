@@ -66,6 +66,7 @@ int hex8_tc32b(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
 int tc3_build_B(const Hex8Operator& op, float** dB);
 int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float4* x4, float4* y4, const float* E32, const unsigned char* mask,
                int epi, const float4* b4, const float4* dinv4, float4* d4, float s0, float s1);
+long long v4_plane_nodes(const LevelGrid& g);  // nodes per plane of a V4 vector (allocation: v4_plane_nodes * nzl float4)
 int vec_st_to_v4(tob_ctx_impl* c, const LevelGrid& g, const double* st, float4* v4);
 int vec_v4_to_st(tob_ctx_impl* c, const LevelGrid& g, const float4* v4, double* st);
 int vec_d2f(tob_ctx_impl* c, const double* a, float* b, long long n);

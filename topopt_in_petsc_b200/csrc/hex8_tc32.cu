@@ -273,6 +273,7 @@ struct Tc2Params {
     float s0, s1;
     int nxn, nyn, nzl, pe, pm;
     long long estride, mstride;
+    long long p4;              // nodes per V4 plane (nxn * nyn rounded up to even: a plane is a whole number of 32-byte units for the halo kernels)
     int zout0, zout1, zchunk;
     int epi;
 };
@@ -417,7 +418,7 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
             float au[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) au[c] = ((m >> c) & 1) ? xs[c] : acc[c];
-            const long long o = ((long long)z * P.nyn + gj) * P.nxn + gi;
+            const long long o = (long long)z * P.p4 + (long long)gj * P.nxn + gi;
             if (P.epi == 0) {
                 P.y[o] = make_float4(au[0], au[1], au[2], 0.0f);
             } else {
@@ -438,34 +439,35 @@ k_hex8_tc32b(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
 }
 
 // ---- V4 (node-interleaved fp32) <-> stored fp64 layout ----------------------------------------------------------------------
+long long v4_plane_nodes(const LevelGrid& g) { return ((long long)g.nxn * g.nyn + 1) & ~1LL; }
 __global__ void k_st_to_v4(const double* __restrict__ st, float4* __restrict__ v4, int nxn, int nyn, int nzl, int px, long long nstride,
-                           long long pstride) {
+                           long long pstride, long long p4) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long long)nxn * nyn * nzl) return;
     const int i = n % nxn, j = (n / nxn) % nyn, k = n / ((long long)nxn * nyn);
     const long long o = (long long)k * pstride + (long long)j * px + i;
-    v4[n] = make_float4((float)st[o], (float)st[o + nstride], (float)st[o + 2 * nstride], 0.0f);
+    v4[(long long)k * p4 + (long long)j * nxn + i] = make_float4((float)st[o], (float)st[o + nstride], (float)st[o + 2 * nstride], 0.0f);
 }
 __global__ void k_v4_to_st(const float4* __restrict__ v4, double* __restrict__ st, int nxn, int nyn, int nzl, int px, long long nstride,
-                           long long pstride, int z0, int z1) {
+                           long long pstride, int z0, int z1, long long p4) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long long)nxn * nyn * nzl) return;
     const int i = n % nxn, j = (n / nxn) % nyn, k = n / ((long long)nxn * nyn);
     if (k < z0 || k >= z1) return;
     const long long o = (long long)k * pstride + (long long)j * px + i;
-    const float4 v = v4[n];
+    const float4 v = v4[(long long)k * p4 + (long long)j * nxn + i];
     st[o] = v.x; st[o + nstride] = v.y; st[o + 2 * nstride] = v.z;
 }
 int vec_st_to_v4(tob_ctx_impl* c, const LevelGrid& g, const double* st, float4* v4) {
     const long long n = (long long)g.nxn * g.nyn * g.nzl();
-    k_st_to_v4<<<div_up(n, 256), 256, 0, c->stream>>>(st, v4, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride);
+    k_st_to_v4<<<div_up(n, 256), 256, 0, c->stream>>>(st, v4, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride, v4_plane_nodes(g));
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;
 }
 int vec_v4_to_st(tob_ctx_impl* c, const LevelGrid& g, const float4* v4, double* st) {
     const long long n = (long long)g.nxn * g.nyn * g.nzl();
-    k_v4_to_st<<<div_up(n, 256), 256, 0, c->stream>>>(v4, st, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride, g.zl_own0(), g.zl_own1());
+    k_v4_to_st<<<div_up(n, 256), 256, 0, c->stream>>>(v4, st, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride, g.zl_own0(), g.zl_own1(), v4_plane_nodes(g));
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;
@@ -501,14 +503,14 @@ int hex8_tc32b(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     CUtensorMap tmX;
     {
         cuuint64_t dims[4] = {4, (cuuint64_t)g.nxn, (cuuint64_t)g.nyn, (cuuint64_t)g.nzl()};
-        cuuint64_t str[3] = {16, (cuuint64_t)g.nxn * 16, (cuuint64_t)g.nxn * g.nyn * 16};
+        cuuint64_t str[3] = {16, (cuuint64_t)g.nxn * 16, (cuuint64_t)v4_plane_nodes(g) * 16};
         cuuint32_t box[4] = {4, T2_PX, T2_PY, 1};
         TOB_CHECK(encode_map(c, &tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x4, dims, str, box));
     }
     Tc2Params P;
     P.y = y4; P.E32 = E32; P.mask = mask; P.B = dB; P.b = b4; P.dinv = dinv4; P.d = d4; P.s0 = s0; P.s1 = s1;
     P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.pe = g.pe; P.pm = g.pm; P.estride = g.estride; P.mstride = g.mstride;
-    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi;
+    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi; P.p4 = v4_plane_nodes(g);
     const int gx = div_up(g.nxn, T2_X), gy = div_up(g.nyn, T2_Y);
     const int nz = P.zout1 - P.zout0;
     int nch = std::max(1, std::min(nz / 8, (int)((6LL * c->num_sms * 2) / std::max(1, gx * gy))));
@@ -662,7 +664,7 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
             float au[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) au[c] = ((m >> c) & 1) ? xs[c] : carry[c] + low[c];
-            const long long o = ((long long)L * P.nyn + gj) * P.nxn + gi;
+            const long long o = (long long)L * P.p4 + (long long)gj * P.nxn + gi;
             if (P.epi == 0) {
                 P.y[o] = make_float4(au[0], au[1], au[2], 0.0f);
             } else {
@@ -702,14 +704,14 @@ int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     CUtensorMap tmX;
     {
         cuuint64_t dims[4] = {4, (cuuint64_t)g.nxn, (cuuint64_t)g.nyn, (cuuint64_t)g.nzl()};
-        cuuint64_t str[3] = {16, (cuuint64_t)g.nxn * 16, (cuuint64_t)g.nxn * g.nyn * 16};
+        cuuint64_t str[3] = {16, (cuuint64_t)g.nxn * 16, (cuuint64_t)v4_plane_nodes(g) * 16};
         cuuint32_t box[4] = {4, T3_PX, T3_PY, 1};
         TOB_CHECK(encode_map(c, &tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x4, dims, str, box));
     }
     Tc2Params P;
     P.y = y4; P.E32 = E32; P.mask = mask; P.B = dB; P.b = b4; P.dinv = dinv4; P.d = d4; P.s0 = s0; P.s1 = s1;
     P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.pe = g.pe; P.pm = g.pm; P.estride = g.estride; P.mstride = g.mstride;
-    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi;
+    P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi; P.p4 = v4_plane_nodes(g);
     const int gx = div_up(g.nxn, T3_EX - 1), gy = div_up(g.nyn, T3_EY - 1);
     const int nz = P.zout1 - P.zout0;
     int nch = std::max(1, std::min(nz / 8, (int)((5LL * c->num_sms * 2) / std::max(1, gx * gy))));
