@@ -9,6 +9,13 @@ __device__ __forceinline__ unsigned long long cg_ld_acquire_sys(const unsigned l
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// bounded spin on a peer-written epoch flag: a peer that died (or never launched) must not hang this GPU for ever -- after ~4 s
+// of SM clock the wait gives up; the sums then contain garbage/NaN and the host's convergence check fails the solve loudly
+__device__ __forceinline__ void cg_wait_flag(const unsigned long long* p, unsigned long long e) {
+    const long long t0 = clock64();
+    while (cg_ld_acquire_sys(p) < e)
+        if (clock64() - t0 > 8000000000LL) break;
+}
 __device__ __forceinline__ void cg_st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -29,7 +36,7 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
                 // the three sums of every rank were stored into my arena by the last CTA of that rank's SpMV
                 const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pe.arena);
                 for (int k = 0; k < pe.n; k++)
-                    while (cg_ld_acquire_sys(&flags[F_CG_RED0 + k]) < st.epoch) {}
+                    cg_wait_flag(&flags[F_CG_RED0 + k], st.epoch);
                 const size_t off = (st.epoch & 1) ? red_off1 : red_off0;
                 gam = rr = del = 0.0;
                 for (int k = 0; k < pe.n; k++) {  // rank order: bitwise identical on every rank

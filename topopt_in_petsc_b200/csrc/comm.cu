@@ -76,8 +76,9 @@ k_halo_p2p(double* __restrict__ v, long long plane, int zl_first_owned, int zl_l
             if (hi) st_release_sys(reinterpret_cast<unsigned long long*>(hi) + F_HALO_FROM_LO, e);
         }
         // phase 2: wait for the neighbours' data of this epoch
-        if (lo) while (ld_acquire_sys(&flags[F_HALO_FROM_LO]) < e) {}
-        if (hi) while (ld_acquire_sys(&flags[F_HALO_FROM_HI]) < e) {}
+        const long long t0 = clock64();  // bounded spins (~4 s): a dead peer must not hang this GPU for ever
+        if (lo) while (ld_acquire_sys(&flags[F_HALO_FROM_LO]) < e && clock64() - t0 < 8000000000LL) {}
+        if (hi) while (ld_acquire_sys(&flags[F_HALO_FROM_HI]) < e && clock64() - t0 < 8000000000LL) {}
     }
     __syncthreads();
     if (lo) {
@@ -129,7 +130,8 @@ k_finalize_p2p(const double* __restrict__ partials, int nblk, double* __restrict
     __syncthreads();
     if (threadIdx.x < n) {
         st_release_sys(reinterpret_cast<unsigned long long*>(peers.p[threadIdx.x]) + F_RED_FLAG0 + rank, e);
-        while (ld_acquire_sys(&flags[F_RED_FLAG0 + threadIdx.x]) < e) {}
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&flags[F_RED_FLAG0 + threadIdx.x]) < e && clock64() - t0 < 8000000000LL) {}
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nvals; i += blockDim.x) {

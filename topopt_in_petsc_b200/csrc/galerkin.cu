@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(256) k_dense_invert(double* __restrict__ D, in
         if (threadIdx.x == 0) {  // grid barrier k (all CTAs are resident: G <= a few per SM)
             __threadfence();
             atomicAdd(cnt, 1u);
-            while (*reinterpret_cast<volatile unsigned int*>(cnt) < (unsigned int)(k + 1) * (unsigned int)G) {}
+            const long long t0 = clock64();  // (bounded: if the CTAs were ever not co-resident the inverse would be garbage, not a hang)
+            while (*reinterpret_cast<volatile unsigned int*>(cnt) < (unsigned int)(k + 1) * (unsigned int)G && clock64() - t0 < 4000000000LL) {}
             __threadfence();
         }
         __syncthreads();

@@ -576,10 +576,11 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 // chunks that read a ghost plane wait (system-scope acquire of the epoch flag in my arena)
                 const unsigned long long e = P.cg->st[P.cgpar].epoch;
                 const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(P.pe.arena);
+                const long long t0 = clock64();  // bounded: a dead neighbour must not hang this GPU (the solve then fails its residual check)
                 if (z0 == P.zout0 && P.pe.rank > 0)
-                    while (ld_acquire_sys_u64(&flags[F_CG_FROM_LO]) < e) {}
+                    while (ld_acquire_sys_u64(&flags[F_CG_FROM_LO]) < e && clock64() - t0 < 8000000000LL) {}
                 if (z1 == P.zout1 && P.pe.rank < P.pe.n - 1)
-                    while (ld_acquire_sys_u64(&flags[F_CG_FROM_HI]) < e) {}
+                    while (ld_acquire_sys_u64(&flags[F_CG_FROM_HI]) < e && clock64() - t0 < 8000000000LL) {}
             }
             for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
             for (int s = 0; s < L::STAGES; s++) mbar_init(&ebars[s], nactive);
