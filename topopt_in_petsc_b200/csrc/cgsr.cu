@@ -20,7 +20,9 @@ __device__ __forceinline__ void cg_st_release_sys(unsigned long long* p, unsigne
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <int MODE>
+// XM: lazy update of the iterate as in vecops.cu -- 1 = even iteration of a pair (x untouched: 9 instead of 11 vector streams),
+// 2 = odd iteration (x += alpha_even p_even + alpha p; p_even is simply the direction this kernel loads), 0 = every iteration
+template <int MODE, int XM>
 __global__ void __launch_bounds__(kFlatThreads)
 k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __restrict__ r, double* __restrict__ u,
             const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s, const double* __restrict__ dinv, long long n,
@@ -79,12 +81,18 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
         double2 rv = r2[i];
         if (MODE == 1) {
             const double2 uv = u2[i], wv = w2[i];
-            double2 pv = p2[i], sv = s2[i], xv = x2[i];
+            double2 pv = p2[i], sv = s2[i];
+            const double2 pe = pv;  // the previous direction (XM == 2: the even iteration's, whose x update was deferred)
             pv.x = fma(beta, pv.x, uv.x); pv.y = fma(beta, pv.y, uv.y);
             sv.x = fma(beta, sv.x, wv.x); sv.y = fma(beta, sv.y, wv.y);
-            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            if (XM != 1) {
+                double2 xv = x2[i];
+                if (XM == 2) { xv.x = fma(st.alpha_prev, pe.x, xv.x); xv.y = fma(st.alpha_prev, pe.y, xv.y); }
+                xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+                x2[i] = xv;
+            }
             rv.x = fma(-alpha, sv.x, rv.x); rv.y = fma(-alpha, sv.y, rv.y);
-            p2[i] = pv; s2[i] = sv; x2[i] = xv; r2[i] = rv;
+            p2[i] = pv; s2[i] = sv; r2[i] = rv;
         }
         const double2 dv = d2[i];
         const double2 un = make_double2(dv.x * rv.x, dv.y * rv.y);
@@ -114,16 +122,16 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
 }
 
 int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, double* r, double* u, const double* w,
-              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers) {
+              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode) {
     const int nb = flat_grid(c, g.own_len);
     const long long o = g.own_off;
     const size_t r0 = peers.n > 1 ? cg_red_off(peers.n, 0, 0) : 0, r1 = peers.n > 1 ? cg_red_off(peers.n, 1, 0) : 0;
-    if (mode == 0)
-        k_cg_update<0><<<nb, kFlatThreads, 0, c->stream>>>(cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride,
-                                                         upart, peers, r0, r1);
-    else
-        k_cg_update<1><<<nb, kFlatThreads, 0, c->stream>>>(cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride,
-                                                         upart, peers, r0, r1);
+#define TOB_CG_ARGS cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride, upart, peers, r0, r1
+    if (mode == 0) k_cg_update<0, 0><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
+    else if (xmode == 1) k_cg_update<1, 1><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
+    else if (xmode == 2) k_cg_update<1, 2><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
+    else k_cg_update<1, 0><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
+#undef TOB_CG_ARGS
     c->launches++;
     TOB_KERNEL_CHECK();
     if (nbU) *nbU = nb;

@@ -52,6 +52,6 @@ void peer_vec_free(tob_ctx_impl* c, PeerVec* v);
 
 // U kernel.  mode 0 = set-up (u = dinv r only, first = 1), mode 1 = iteration.  par = parity of the state it reads.
 int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, double* r, double* u, const double* w,
-              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers);
+              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode = 0);
 
 }  // namespace tob

@@ -150,8 +150,9 @@ static int elast_pcg_sr(tob_elast_impl* h, double tol, double bnorm, int* it_out
     h->sr_par = 1;
     TOB_CHECK(elast_apply(h, u, h->Q, EPI_CGDOT, false, 0, nullptr, &np));
     int par = 1, it = 0;
-    auto one_iteration = [&]() -> int {
-        TOB_CHECK(cg_update(c, g, h->sr_cg, par, 1, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV, h->sr_upart, &h->sr_nbU, h->sr_pe));
+    static const bool lazyx = !(getenv("TOB_PCG_LAZYX") && atoi(getenv("TOB_PCG_LAZYX")) == 0);
+    auto one_iteration = [&](int xm) -> int {  // xm: 1 = even, 2 = odd iteration of a pair (lazy x update, cgsr.cu)
+        TOB_CHECK(cg_update(c, g, h->sr_cg, par, 1, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV, h->sr_upart, &h->sr_nbU, h->sr_pe, lazyx ? xm : 0));
         c->cg_epoch++;
         par ^= 1;
         h->sr_par = par;
@@ -166,8 +167,8 @@ static int elast_pcg_sr(tob_elast_impl* h, double tol, double bnorm, int* it_out
     double rnorm = *rnorm_out;
     double* hs = c->h_scalars + 40;
     while (it < o.maxits) {
-        TOB_CHECK(one_iteration());
-        TOB_CHECK(one_iteration());
+        TOB_CHECK(one_iteration(1));
+        TOB_CHECK(one_iteration(2));
         it += 2;
         if (graphed) {
             if (!h->sr_graph || h->sr_graph_its != blk) {
@@ -178,7 +179,7 @@ static int elast_pcg_sr(tob_elast_impl* h, double tol, double bnorm, int* it_out
                 const unsigned long long e0 = c->cg_epoch;
                 TOB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                 int rc = 0;
-                for (int k = 0; k < blk && !rc; k++) rc = one_iteration();
+                for (int k = 0; k < blk && !rc; k++) rc = one_iteration(1 + (k & 1));
                 cudaGraph_t graph = nullptr;
                 cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
                 h->profile = prof;
@@ -248,18 +249,21 @@ int elast_pcg(tob_elast_impl* h) {
         TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, nullptr, nullptr));
         const int check = o.check_every > 0 ? o.check_every : 10;
         const bool graphed1 = !getenv("TOB_PCG_NOGRAPH") && check >= 4;
-        auto one_iteration1 = [&](double* bc, double* bn) -> int {
+        // iterations run in (even, odd) pairs with the lazy x update of vecops.cu (xm = 1, 2); TOB_PCG_LAZYX=0 switches it off
+        static const bool lazyx = !(getenv("TOB_PCG_LAZYX") && atoi(getenv("TOB_PCG_LAZYX")) == 0);
+        double* ab = c->d_scalars + 12;
+        auto one_iteration1 = [&](double* bc, double* bn, int xm) -> int {
             TOB_CHECK(elast_apply(h, h->P, h->Q, EPI_DOT, false, 0, nullptr, &np));
-            TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV32, c->d_partials, np, bc, bn, &nbx));
-            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, bn, bc));
+            TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV32, c->d_partials, np, bc, bn, &nbx, lazyx ? xm : 0, ab));
+            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, bn, bc, ab));
             return 0;
         };
         const int stride_saved1 = h->prof_stride;
         if (graphed1) h->prof_stride = 1;  // the two eager iterations per round are the timed sample
         while (graphed1 && it < o.maxits) {
             // same scheme as the multi-GPU path below: 2 eager (timed) iterations, then a replayed graph of `check`
-            TOB_CHECK(one_iteration1(blk_cur, blk_nxt));
-            TOB_CHECK(one_iteration1(blk_nxt, blk_cur));
+            TOB_CHECK(one_iteration1(blk_cur, blk_nxt, 1));
+            TOB_CHECK(one_iteration1(blk_nxt, blk_cur, 2));
             it += 2;
             const int blk = check & ~1;
             if (!h->pcg_graph || h->pcg_graph_its != blk) {
@@ -270,8 +274,8 @@ int elast_pcg(tob_elast_impl* h) {
                 TOB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
                 int rc = 0;
                 for (int k = 0; k < blk && !rc; k += 2) {
-                    rc = one_iteration1(blk_cur, blk_nxt);
-                    if (!rc) rc = one_iteration1(blk_nxt, blk_cur);
+                    rc = one_iteration1(blk_cur, blk_nxt, 1);
+                    if (!rc) rc = one_iteration1(blk_nxt, blk_cur, 2);
                 }
                 cudaGraph_t graph = nullptr;
                 cudaError_t e = cudaStreamEndCapture(c->stream, &graph);

@@ -323,11 +323,16 @@ __device__ __forceinline__ double sum_parts_bcast(const double* __restrict__ p, 
 }
 
 // H = L2 hint mask (common.cuh): bit 0 streams evict_first, bit 1 p evict_last, bit 2 q last-use / r keep
-template <int H>
+// XM = how the iterate is updated.  0: x += alpha p every iteration.  1 / 2: LAZY x -- iterations come in (even, odd) pairs; the
+// even one leaves x alone (it does not even read x or p: 3.5 instead of 6.5 vector streams) and parks its alpha in ab[0]; the odd
+// one applies both updates at once,  x += alpha_even p_even + alpha p,  recovering  p_even = (p - z) / beta  from the direction
+// recurrence p = z + beta p_even (z = D^-1 r with the r this kernel starts from, beta = ab[1] left by the p-update kernel).
+// A pair moves 10 vector streams instead of 13.  The solver only stops after complete pairs.
+template <int H, int XM>
 __global__ void __launch_bounds__(kFlatThreads)
 k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
                   const float* __restrict__ dinv, long long n, const double* __restrict__ pq_parts, int n_pq,
-                  const double* __restrict__ prev_parts, int nb_prev, double* __restrict__ out_parts) {
+                  const double* __restrict__ prev_parts, int nb_prev, double* __restrict__ out_parts, double* __restrict__ ab) {
     __shared__ double red[32];
     __shared__ double bc;
     double alpha = 0.0;  // pq_parts == nullptr: the initial pass that only forms r.r and r.dinv.r
@@ -336,6 +341,9 @@ k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* 
         const double rz = sum_parts_bcast(prev_parts + nb_prev, nb_prev, red, &bc);
         alpha = rz / pq;
     }
+    double a_even = 0.0, inv_beta = 0.0;
+    if (XM == 1 && blockIdx.x == 0 && threadIdx.x == 0) ab[0] = alpha;
+    if (XM == 2) { a_even = ab[0]; inv_beta = 1.0 / ab[1]; }
     const uint64_t pf = l2_policy_first(), pl = l2_policy_last();
     double rr = 0.0, rz2 = 0.0;
     long long n2 = n >> 1;
@@ -346,17 +354,23 @@ k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* 
     const float2* d2 = reinterpret_cast<const float2*>(dinv);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
         double2 rv = (H & 1) ? ld2_hint(r2 + i, pf) : r2[i];
-        if (pq_parts) {
-            double2 xv = (H & 1) ? ld2_hint(x2 + i, pf) : x2[i];
-            const double2 pv = (H & 2) ? ld2_hint(p2 + i, pl) : p2[i];
-            const double2 qv = (H & 4) ? ld2_hint(q2 + i, pf) : q2[i];
-            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
-            rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
-            if (H & 1) st2_hint(x2 + i, xv, pf); else x2[i] = xv;
-            if ((H & 1) && !(H & 4)) st2_hint(r2 + i, rv, pf); else r2[i] = rv;  // bit 2: keep the new r for update_p
-        }
         const float2 dvf = __ldcs(d2 + i);  // the Jacobi preconditioner is stored in single precision (any SPD diagonal is a valid
         const double2 dv = make_double2((double)dvf.x, (double)dvf.y);  // preconditioner; 4 instead of 8 bytes per dof in two of the three kernels)
+        if (pq_parts) {
+            const double2 qv = (H & 4) ? ld2_hint(q2 + i, pf) : q2[i];
+            if (XM != 1) {
+                double2 xv = (H & 1) ? ld2_hint(x2 + i, pf) : x2[i];
+                const double2 pv = (H & 2) ? ld2_hint(p2 + i, pl) : p2[i];
+                if (XM == 2) {  // the deferred update of the even iteration: p_even = (p - D^-1 r) / beta
+                    xv.x = fma(a_even * inv_beta, pv.x - dv.x * rv.x, xv.x);
+                    xv.y = fma(a_even * inv_beta, pv.y - dv.y * rv.y, xv.y);
+                }
+                xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+                if (H & 1) st2_hint(x2 + i, xv, pf); else x2[i] = xv;
+            }
+            rv.x = fma(-alpha, qv.x, rv.x); rv.y = fma(-alpha, qv.y, rv.y);
+            if ((H & 1) && !(H & 4)) st2_hint(r2 + i, rv, pf); else r2[i] = rv;  // bit 2: keep the new r for update_p
+        }
         rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
         rz2 = fma(rv.x * dv.x, rv.x, rz2); rz2 = fma(rv.y * dv.y, rv.y, rz2);
     }
@@ -368,7 +382,7 @@ k_pcg_update_xr_f(double* __restrict__ x, double* __restrict__ r, const double* 
 template <int H>
 __global__ void __launch_bounds__(kFlatThreads)
 k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const float* __restrict__ dinv, long long n,
-                 const double* __restrict__ new_parts, const double* __restrict__ old_parts, int nb) {
+                 const double* __restrict__ new_parts, const double* __restrict__ old_parts, int nb, double* __restrict__ ab) {
     __shared__ double red[32];
     __shared__ double bc;
     double beta = 0.0;  // old_parts == nullptr: first direction p = dinv r
@@ -376,6 +390,7 @@ k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const flo
         const double rz_new = sum_parts_bcast(new_parts + nb, nb, red, &bc);
         const double rz_old = sum_parts_bcast(old_parts + nb, nb, red, &bc);
         beta = rz_new / rz_old;
+        if (ab && blockIdx.x == 0 && threadIdx.x == 0) ab[1] = beta;  // the lazy-x update of the next iteration needs it
     }
     const uint64_t pf = l2_policy_first(), pl = l2_policy_last();
     long long n2 = n >> 1;
@@ -401,20 +416,23 @@ k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const flo
     }
 
 int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const float* dinv,
-                    const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out) {
+                    const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out, int xmode, double* ab) {
     const int nb = flat_grid(c, g.own_len);
-    TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM><<<nb, kFlatThreads, 0, c->stream>>>(
-        x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off, dinv + g.own_off, g.own_len, pq_parts, n_pq, prev_parts, nb, out_parts)));
+#define TOB_XR_ARGS x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off, dinv + g.own_off, g.own_len, pq_parts, n_pq, prev_parts, nb, out_parts, ab
+    if (xmode == 1) { TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM, 1><<<nb, kFlatThreads, 0, c->stream>>>(TOB_XR_ARGS))); }
+    else if (xmode == 2) { TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM, 2><<<nb, kFlatThreads, 0, c->stream>>>(TOB_XR_ARGS))); }
+    else { TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM, 0><<<nb, kFlatThreads, 0, c->stream>>>(TOB_XR_ARGS))); }
+#undef TOB_XR_ARGS
     c->launches++;
     TOB_KERNEL_CHECK();
     if (nb_out) *nb_out = nb;
     return 0;
 }
 int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const float* dinv, const double* new_parts,
-                   const double* old_parts) {
+                   const double* old_parts, double* ab) {
     const int nb = flat_grid(c, g.own_len);
     TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_p_f<HM><<<nb, kFlatThreads, 0, c->stream>>>(p + g.own_off, r + g.own_off, dinv + g.own_off,
-                                                                                     g.own_len, new_parts, old_parts, nb)));
+                                                                                     g.own_len, new_parts, old_parts, nb, ab)));
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;

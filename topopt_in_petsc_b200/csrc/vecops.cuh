@@ -18,8 +18,9 @@ int vec_fill(tob_ctx_impl* c, double* y, double v, long long n);
 int vec_restore_fixed(tob_ctx_impl* c, double* y, const double* u, const double* nf, long long n);
 // single-rank Jacobi-PCG kernels that consume per-CTA partial sums directly (no finalize launches)
 int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const float* dinv,
-                    const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out);
+                    const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out, int xmode = 0,
+                    double* ab = nullptr);
 int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const float* dinv, const double* new_parts,
-                   const double* old_parts);
+                   const double* old_parts, double* ab = nullptr);
 int finalize_parts(tob_ctx_impl* c, const double* parts, int nb, int slot);
 }  // namespace tob
