@@ -387,6 +387,7 @@ def test_galerkin_coarse_operators_match_ptap(oracle, monkeypatch):
     import scipy.sparse as sp
     from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
     monkeypatch.setenv("TOB_GMG_GALERKIN_FROM", "1")
+    monkeypatch.setenv("TOB_GMG_STENCIL_FP64", "1")  # the coefficients are stored in fp32 by default (a preconditioner); exact parity in fp64
     rng = np.random.default_rng(21)
     shape = (17, 9, 13)
     g = oracle.Grid(*shape)
@@ -408,6 +409,8 @@ def test_galerkin_coarse_operators_match_ptap(oracle, monkeypatch):
         ref = (D @ (P.T @ A_prev @ P) @ D + sp.diags(1.0 - Nc)).tocsr()
         got = mg.GmgLevelMatrix(lvl)
         assert got is not None
+        if lvl == 1:
+            got1 = got
         assert abs(got - ref).max() <= 1e-12 * abs(ref).max(), (lvl, abs(got - ref).max() / abs(ref).max())
         # the next level is the product of THIS level's operator without its Dirichlet rows: rebuild the unconstrained one
         A_prev, dims = (P.T @ A_prev @ P).tocsr(), nc
@@ -419,7 +422,17 @@ def test_galerkin_coarse_operators_match_ptap(oracle, monkeypatch):
     st = mg.SolveState(x, 1e-9, 1.0, 3.0)
     assert st.rel_residual <= 1e-8 and st.iterations < 200, st.iterations  # a random cubed field on 16x8x12 elements is a hard, tiny case
     assert np.abs(mg.GetStateField() - U).max() <= 1e-5 * np.abs(U).max()
-    mg.close(); ctx.close()
+    mg.close()
+    # default storage (fp32 coefficients): the same operators to single precision, the same solution
+    monkeypatch.setenv("TOB_GMG_STENCIL_FP64", "0")
+    mg32 = LinearElasticity(ctx, opts=solver_opts(pc=1, nlvls=3, rtol=1e-8, maxits=200))
+    mg32.SetDensity(x, 1e-9, 1.0, 3.0)
+    got32 = mg32.GmgLevelMatrix(1)
+    assert abs(got32 - got1).max() <= 1e-6 * abs(got1).max()
+    st32 = mg32.SolveState(x, 1e-9, 1.0, 3.0)
+    assert st32.rel_residual <= 1e-8 and st32.iterations <= st.iterations + 5
+    assert np.abs(mg32.GetStateField() - U).max() <= 1e-5 * np.abs(U).max()
+    mg32.close(); ctx.close()
 
 
 @pytest.mark.parametrize("shape,xc", [((9, 5, 5), (0, 2, 0, 1, 0, 1)), ((34, 21, 13), (0, 2, 0, 1, 0, 1)), ((65, 33, 33), (0, 2, 0, 1, 0, 1)),

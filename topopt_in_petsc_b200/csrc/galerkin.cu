@@ -43,8 +43,9 @@ void galerkin_child_matrices(const double* KE_fine, double* M /* [8][24][24] */)
 
 // ---- assembly from a matrix-free parent ----------------------------------------------------------------------------------
 // one CTA per coarse node, thread t < 243 owns entry (o, c, c2) of its stencil row block
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_galerkin_mf(const double* __restrict__ Ef, const double* __restrict__ M, const unsigned char* __restrict__ maskc, double* __restrict__ A,
+k_galerkin_mf(const double* __restrict__ Ef, const double* __restrict__ M, const unsigned char* __restrict__ maskc, T* __restrict__ A,
               int ncx, int ncy, int ncz, int pxc, int pmc, long long msc, int nfex, int nfey, int nfez, int pef, long long esf,
               long long nnp) {
     const int I = blockIdx.x, J = blockIdx.y, K = blockIdx.z;
@@ -79,7 +80,7 @@ k_galerkin_mf(const double* __restrict__ Ef, const double* __restrict__ M, const
         const bool fr = (mr >> c) & 1, fc = (mc >> c2) & 1;
         if (fr || fc) acc = (o == 13 && c == c2 && fr) ? 1.0 : 0.0;
     }
-    A[(long long)t * nnp + n] = acc;
+    A[(long long)t * nnp + n] = (T)acc;
 }
 
 // ---- assembly from an assembled parent stencil: A_c = P^T A_f P ------------------------------------------------------------
@@ -87,8 +88,9 @@ __device__ __forceinline__ double q1w(int fine, int coarse) {  // 1-D interpolat
     const int d = fine - 2 * coarse;
     return d == 0 ? 1.0 : ((d == 1 || d == -1) ? 0.5 : 0.0);
 }
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_galerkin_st(const double* __restrict__ Af, const unsigned char* __restrict__ maskc, double* __restrict__ Ac, int nfx, int nfy, int nfz,
+k_galerkin_st(const T* __restrict__ Af, const unsigned char* __restrict__ maskc, T* __restrict__ Ac, int nfx, int nfy, int nfz,
               int pxf, long long nnpf, int ncx, int ncy, int ncz, int pxc, int pmc, long long msc, long long nnpc) {
     const int I = blockIdx.x, J = blockIdx.y, K = blockIdx.z;
     const int t = threadIdx.x;
@@ -122,7 +124,7 @@ k_galerkin_st(const double* __restrict__ Af, const unsigned char* __restrict__ m
                                 const double wx = q1w(fi + oi, I2);
                                 if (wx == 0.0 || fi + oi < 0 || fi + oi >= nfx) continue;
                                 const int of = ((ok + 1) * 3 + (oj + 1)) * 3 + (oi + 1);
-                                s = fma(wx * wy * wz, Af[(long long)(of * 9 + q) * nnpf + nf], s);
+                                s = fma(wx * wy * wz, (double)Af[(long long)(of * 9 + q) * nnpf + nf], s);
                             }
                         }
                     }
@@ -135,14 +137,14 @@ k_galerkin_st(const double* __restrict__ Af, const unsigned char* __restrict__ m
         const bool fr = (mr >> c) & 1, fc = (mc >> c2) & 1;
         if (fr || fc) acc = (o == 13 && c == c2 && fr) ? 1.0 : 0.0;
     }
-    Ac[(long long)t * nnpc + n] = acc;
+    Ac[(long long)t * nnpc + n] = (T)acc;
 }
 
 // ---- y = A x with the epilogues of the matrix-free kernel (one thread per node) -------------------------------------------
 // coef: device array {s0, s1} pairs of the Chebyshev recurrence (EPI_CHEB), indexed by `step`
-template <int EPI>
+template <int EPI, typename T>
 __global__ void __launch_bounds__(128)
-k_stencil_apply(const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ a0,
+k_stencil_apply(const T* __restrict__ A, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ a0,
                 const double* __restrict__ a1, double* __restrict__ o1, const double* __restrict__ coef, int step, int nx, int ny, int nz,
                 int px, long long nstride, long long pstride, long long nnp, double* __restrict__ partials) {
     __shared__ double red[32];
@@ -167,10 +169,10 @@ k_stencil_apply(const double* __restrict__ A, const double* __restrict__ x, doub
                     const int o = ((dk + 1) * 3 + (dj + 1)) * 3 + (di + 1);
                     const long long xo = (long long)kk * pstride + (long long)jj * px + ii;
                     const double x0 = x[xo], x1 = x[xo + nstride], x2 = x[xo + 2 * nstride];
-                    const double* Ao = A + (long long)(o * 9) * nnp + n;
+                    const T* Ao = A + (long long)(o * 9) * nnp + n;
 #pragma unroll
                     for (int c = 0; c < 3; c++)
-                        acc[c] = fma(Ao[(long long)(3 * c) * nnp], x0, fma(Ao[(long long)(3 * c + 1) * nnp], x1, fma(Ao[(long long)(3 * c + 2) * nnp], x2, acc[c])));
+                        acc[c] = fma((double)Ao[(long long)(3 * c) * nnp], x0, fma((double)Ao[(long long)(3 * c + 1) * nnp], x1, fma((double)Ao[(long long)(3 * c + 2) * nnp], x2, acc[c])));
                 }
             }
         }
@@ -207,7 +209,11 @@ int stencil_apply(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid& g, in
     dim3 grid(div_up(g.nxn, 128), g.nyn, g.nzn);
     const long long nb = (long long)grid.x * grid.y * grid.z;
     if (nb > kMaxPartials) TOB_FAIL("stencil level too large for the partial-sum buffer");
-#define TOB_ST_LAUNCH(E) k_stencil_apply<E><<<grid, 128, 0, c->stream>>>(S.A, x, y, a0, a1, o1, S.coef, step, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp, c->d_partials)
+#define TOB_ST_LAUNCH(E)                                                                                                              \
+    do {                                                                                                                              \
+        if (S.fp32) k_stencil_apply<E, float><<<grid, 128, 0, c->stream>>>((const float*)S.A, x, y, a0, a1, o1, S.coef, step, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp, c->d_partials); \
+        else k_stencil_apply<E, double><<<grid, 128, 0, c->stream>>>((const double*)S.A, x, y, a0, a1, o1, S.coef, step, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp, c->d_partials); \
+    } while (0)
     switch (epi) {
         case EPI_Y: TOB_ST_LAUNCH(EPI_Y); break;
         case EPI_DOT: TOB_ST_LAUNCH(EPI_DOT); break;
@@ -222,14 +228,15 @@ int stencil_apply(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid& g, in
 }
 
 // ---- diagonal, eigenvalue estimate, Chebyshev coefficients -----------------------------------------------------------------
-__global__ void k_stencil_diag(const double* __restrict__ A, double* __restrict__ dinv, int nx, int ny, int nz, int px, long long nstride,
+template <typename T>
+__global__ void k_stencil_diag(const T* __restrict__ A, double* __restrict__ dinv, int nx, int ny, int nz, int px, long long nstride,
                                long long pstride, long long nnp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, k = blockIdx.z;
     if (i >= nx) return;
     const long long n = ((long long)k * ny + j) * px + i;
     for (int c = 0; c < 3; c++) {
-        const double d = A[(long long)(13 * 9 + 4 * c) * nnp + n];
+        const double d = (double)A[(long long)(13 * 9 + 4 * c) * nnp + n];
         dinv[(long long)k * pstride + c * nstride + (long long)j * px + i] = d != 0.0 ? 1.0 / d : 1.0;
     }
 }
@@ -293,8 +300,9 @@ int stencil_cheb_first(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid& 
 
 // ---- coarsest level: Jacobi-PCG to a relative residual inside ONE CTA (no launches, no host) ----------------------------
 // x = A^-1 b approximately: stops at ||r|| <= rtol ||b|| or maxit.  Work vectors r, p, q in global memory (L1-resident).
+template <typename T>
 __global__ void __launch_bounds__(1024)
-k_coarse_cg(const double* __restrict__ A, const double* __restrict__ dinv, const double* __restrict__ b, double* __restrict__ x,
+k_coarse_cg(const T* __restrict__ A, const double* __restrict__ dinv, const double* __restrict__ b, double* __restrict__ x,
             double* __restrict__ r, double* __restrict__ p, double* __restrict__ q, int nx, int ny, int nz, int px, long long nstride,
             long long pstride, long long nnp, double rtol, int maxit, int* __restrict__ its_out) {
     __shared__ double red[32];
@@ -343,8 +351,8 @@ k_coarse_cg(const double* __restrict__ A, const double* __restrict__ dinv, const
                         if (ii < 0 || ii >= nx) continue;
                         const int o = ((dk + 1) * 3 + (dj + 1)) * 3 + (di + 1);
                         const long long xo = (long long)kk * pstride + (long long)jj * px + ii;
-                        const double* Ao = A + (long long)(o * 9 + 3 * c) * nnp + n;
-                        acc = fma(Ao[0], p[xo], fma(Ao[nnp], p[xo + nstride], fma(Ao[2 * nnp], p[xo + 2 * nstride], acc)));
+                        const T* Ao = A + (long long)(o * 9 + 3 * c) * nnp + n;
+                        acc = fma((double)Ao[0], p[xo], fma((double)Ao[nnp], p[xo + nstride], fma((double)Ao[2 * nnp], p[xo + 2 * nstride], acc)));
                     }
                 }
             }
@@ -379,7 +387,8 @@ k_coarse_cg(const double* __restrict__ A, const double* __restrict__ dinv, const
 
 int stencil_coarse_solve(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid& g, const double* dinv, const double* b, double* x, double* r,
                          double* p, double* q, double rtol, int maxit) {
-    k_coarse_cg<<<1, 1024, 0, c->stream>>>(S.A, dinv, b, x, r, p, q, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp, rtol, maxit, S.its);
+    if (S.fp32) k_coarse_cg<float><<<1, 1024, 0, c->stream>>>((const float*)S.A, dinv, b, x, r, p, q, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp, rtol, maxit, S.its);
+    else k_coarse_cg<double><<<1, 1024, 0, c->stream>>>((const double*)S.A, dinv, b, x, r, p, q, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp, rtol, maxit, S.its);
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;
@@ -391,7 +400,8 @@ int stencil_coarse_solve(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid
 // in-place Gauss-Jordan sweep inside one CTA (SPD: no pivoting), and every V-cycle's coarse solve is one dense
 // matrix-vector product in one launch -- exact, hence a linear preconditioner (the round-1 fixed-count CG was neither), and
 // ~3 us instead of ~400.
-__global__ void __launch_bounds__(256) k_stencil_to_dense(const double* __restrict__ A, double* __restrict__ D, int nx, int ny, int nz, int px,
+template <typename T>
+__global__ void __launch_bounds__(256) k_stencil_to_dense(const T* __restrict__ A, double* __restrict__ D, int nx, int ny, int nz, int px,
                                                           long long nnp, int n) {
     // one CTA per dense row (dof 3*node + c, node = i + nx (j + ny k))
     const int row = blockIdx.x, node = row / 3, c = row % 3;
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(256) k_stencil_to_dense(const double* __restri
         const int di = o % 3 - 1, dj = (o / 3) % 3 - 1, dk = o / 9 - 1;
         const int ii = i + di, jj = j + dj, kk = k + dk;
         if (ii < 0 || ii >= nx || jj < 0 || jj >= ny || kk < 0 || kk >= nz) continue;
-        D[(long long)row * n + 3 * (ii + nx * (jj + ny * kk)) + c2] = A[(long long)(o * 9 + 3 * c + c2) * nnp + nn];
+        D[(long long)row * n + 3 * (ii + nx * (jj + ny * kk)) + c2] = (double)A[(long long)(o * 9 + 3 * c + c2) * nnp + nn];
     }
 }
 // In-place Gauss-Jordan inversion (SPD, no pivoting) on G co-resident CTAs: every CTA keeps RB rows in shared memory; per pivot
@@ -485,7 +495,8 @@ int stencil_dense_setup(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S) {
     if (n > kDenseCoarseMax) return 0;  // too large: the caller keeps the iterative coarse solve
     if (!S.Ainv) TOB_CUDA(cudaMalloc(&S.Ainv, sizeof(double) * (size_t)n * n));
     S.ndense = n;
-    k_stencil_to_dense<<<n, 256, 0, c->stream>>>(S.A, S.Ainv, g.nxn, g.nyn, g.nzn, g.px, S.nnp, n);
+    if (S.fp32) k_stencil_to_dense<float><<<n, 256, 0, c->stream>>>((const float*)S.A, S.Ainv, g.nxn, g.nyn, g.nzn, g.px, S.nnp, n);
+    else k_stencil_to_dense<double><<<n, 256, 0, c->stream>>>((const double*)S.A, S.Ainv, g.nxn, g.nyn, g.nzn, g.px, S.nnp, n);
     if (!S.prow) {
         TOB_CUDA(cudaMalloc(&S.prow, sizeof(double) * 2 * kDenseCoarseMax));
         TOB_CUDA(cudaMalloc(&S.bar, sizeof(unsigned int)));
@@ -507,8 +518,12 @@ int stencil_dense_solve(tob_ctx_impl* c, const StencilLevel& S, const LevelGrid&
 // ---- level management --------------------------------------------------------------------------------------------------------
 int stencil_alloc(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S) {
     S.nnp = (long long)g.nzn * g.nyn * g.px;
-    TOB_CUDA(cudaMalloc(&S.A, sizeof(double) * 243 * S.nnp));
-    TOB_CUDA(cudaMemsetAsync(S.A, 0, sizeof(double) * 243 * S.nnp, c->stream));
+    // coefficients in single precision by default: the level is a preconditioner, and its SpMV is pure coefficient streaming
+    // (1944 B per node in fp64); TOB_GMG_STENCIL_FP64=1 keeps doubles (the Galerkin parity test does)
+    S.fp32 = !(getenv("TOB_GMG_STENCIL_FP64") && atoi(getenv("TOB_GMG_STENCIL_FP64")) != 0);
+    const size_t esz = S.fp32 ? sizeof(float) : sizeof(double);
+    TOB_CUDA(cudaMalloc(&S.A, esz * 243 * S.nnp));
+    TOB_CUDA(cudaMemsetAsync(S.A, 0, esz * 243 * S.nnp, c->stream));
     TOB_CUDA(cudaMalloc(&S.coef, sizeof(double) * 2 * 16));
     TOB_CUDA(cudaMalloc(&S.lam, sizeof(double)));
     TOB_CUDA(cudaMalloc(&S.its, sizeof(int)));
@@ -531,7 +546,9 @@ int stencil_assemble_from_mf(tob_ctx_impl* c, const LevelGrid& gf, const double*
         TOB_CUDA(cudaMemcpy(S.M, M.data(), sizeof(double) * M.size(), cudaMemcpyHostToDevice));
     }
     dim3 grid(gc.nxn, gc.nyn, gc.nzn);
-    k_galerkin_mf<<<grid, 256, 0, c->stream>>>(Ef, S.M, maskc, S.A, gc.nxn, gc.nyn, gc.nzn, gc.px, gc.pm, gc.mstride, gf.nex, gf.ney, gf.nez,
+    if (S.fp32) k_galerkin_mf<float><<<grid, 256, 0, c->stream>>>(Ef, S.M, maskc, (float*)S.A, gc.nxn, gc.nyn, gc.nzn, gc.px, gc.pm, gc.mstride, gf.nex, gf.ney, gf.nez,
+                                               gf.pe, gf.estride, S.nnp);
+    else k_galerkin_mf<double><<<grid, 256, 0, c->stream>>>(Ef, S.M, maskc, (double*)S.A, gc.nxn, gc.nyn, gc.nzn, gc.px, gc.pm, gc.mstride, gf.nex, gf.ney, gf.nez,
                                                gf.pe, gf.estride, S.nnp);
     c->launches++;
     TOB_KERNEL_CHECK();
@@ -540,7 +557,10 @@ int stencil_assemble_from_mf(tob_ctx_impl* c, const LevelGrid& gf, const double*
 int stencil_assemble_from_stencil(tob_ctx_impl* c, const LevelGrid& gf, const StencilLevel& F, const LevelGrid& gc, const unsigned char* maskc,
                                   StencilLevel& S) {
     dim3 grid(gc.nxn, gc.nyn, gc.nzn);
-    k_galerkin_st<<<grid, 256, 0, c->stream>>>(F.A, maskc, S.A, gf.nxn, gf.nyn, gf.nzn, gf.px, F.nnp, gc.nxn, gc.nyn, gc.nzn, gc.px, gc.pm,
+    if (F.fp32 != S.fp32) TOB_FAIL("internal: Galerkin levels with different storage precision");
+    if (S.fp32) k_galerkin_st<float><<<grid, 256, 0, c->stream>>>((const float*)F.A, maskc, (float*)S.A, gf.nxn, gf.nyn, gf.nzn, gf.px, F.nnp, gc.nxn, gc.nyn, gc.nzn, gc.px, gc.pm,
+                                               gc.mstride, S.nnp);
+    else k_galerkin_st<double><<<grid, 256, 0, c->stream>>>((const double*)F.A, maskc, (double*)S.A, gf.nxn, gf.nyn, gf.nzn, gf.px, F.nnp, gc.nxn, gc.nyn, gc.nzn, gc.px, gc.pm,
                                                gc.mstride, S.nnp);
     c->launches++;
     TOB_KERNEL_CHECK();
@@ -550,7 +570,8 @@ int stencil_assemble_from_stencil(tob_ctx_impl* c, const LevelGrid& gf, const St
 // dinv, lambda_max(D^-1 A) by `nit` power iterations (all on the device), Chebyshev coefficients for `deg` steps
 int stencil_finish(tob_ctx_impl* c, const LevelGrid& g, StencilLevel& S, double* dinv, double ratio, int deg, int nit) {
     dim3 grid(div_up(g.nxn, 128), g.nyn, g.nzn);
-    k_stencil_diag<<<grid, 128, 0, c->stream>>>(S.A, dinv, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp);
+    if (S.fp32) k_stencil_diag<float><<<grid, 128, 0, c->stream>>>((const float*)S.A, dinv, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp);
+    else k_stencil_diag<double><<<grid, 128, 0, c->stream>>>((const double*)S.A, dinv, g.nxn, g.nyn, g.nzn, g.px, g.nstride, g.pstride, S.nnp);
     c->launches++;
     TOB_KERNEL_CHECK();
     if (!S.pv_init) {

@@ -5,7 +5,8 @@
 namespace tob {
 
 struct StencilLevel {
-    double* A = nullptr;     // [243][nnp]: k = 9 * offset + 3 * c + c2, offset = ((dk+1)*3 + (dj+1))*3 + (di+1)
+    void* A = nullptr;       // [243][nnp] float (default) or double: k = 9 * offset + 3 * c + c2, offset = ((dk+1)*3 + (dj+1))*3 + (di+1)
+    bool fp32 = true;
     long long nnp = 0;       // nzn * nyn * px nodes (x padded like the nodal vectors)
     double* coef = nullptr;  // Chebyshev {s0, s1} pairs (device; refreshed with the operator)
     double* lam = nullptr;   // power-iteration estimate of lambda_max(D^-1 A)

@@ -650,8 +650,16 @@ extern "C" int tob_elast_gmg_level_stencil(tob_elast* hh, int level, double* out
     if (dims) { dims[0] = L.g.nxn; dims[1] = L.g.nyn; dims[2] = L.g.nzn; dims[3] = L.g.px; }
     if (is_stencil) *is_stencil = L.stencil ? 1 : 0;
     if (out && L.stencil) {
-        TOB_CUDA(cudaMemcpyAsync(out, L.S.A, sizeof(double) * 243 * L.S.nnp, cudaMemcpyDeviceToHost, h->c->stream));
-        TOB_CUDA(cudaStreamSynchronize(h->c->stream));
+        const size_t cnt = (size_t)243 * L.S.nnp;
+        if (L.S.fp32) {
+            std::vector<float> tmp(cnt);
+            TOB_CUDA(cudaMemcpyAsync(tmp.data(), L.S.A, sizeof(float) * cnt, cudaMemcpyDeviceToHost, h->c->stream));
+            TOB_CUDA(cudaStreamSynchronize(h->c->stream));
+            for (size_t i = 0; i < cnt; i++) out[i] = tmp[i];
+        } else {
+            TOB_CUDA(cudaMemcpyAsync(out, L.S.A, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->c->stream));
+            TOB_CUDA(cudaStreamSynchronize(h->c->stream));
+        }
     }
     return 0;
 }
