@@ -549,7 +549,7 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sP = smem + T3_B_BYTES;                     // 4 plane slots
-    float4* sY = reinterpret_cast<float4*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // 2 x [8][128]
+    float4* sY = reinterpret_cast<float4*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // [8][128] (one buffer: occupancy beats the saved barrier)
     __shared__ __align__(8) uint64_t full[4];
     __shared__ __align__(8) uint64_t mma_done[2];  // one per TMEM accumulator (the MMAs run one layer ahead of the epilogue)
     __shared__ uint32_t tmem_base_s;
@@ -622,7 +622,7 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         const int buf = (L - pfirst) & 1;
         mbar_wait(&mma_done[buf], (uint32_t)(((L - pfirst) >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float4* Yb = sY + (L & 1) * (8 * 128);
+        float4* Yb = sY;
         {
             uint32_t d[32];
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(32 * buf);
@@ -678,8 +678,8 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) carry[c] = up[c];
+        __syncthreads();  // the node sums are done with the transposed buffer
     }
-    __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
 }
 
@@ -714,10 +714,20 @@ int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1(); P.epi = epi; P.p4 = v4_plane_nodes(g);
     const int gx = div_up(g.nxn, T3_EX - 1), gy = div_up(g.nyn, T3_EY - 1);
     const int nz = P.zout1 - P.zout0;
-    int nch = std::max(1, std::min(nz / 8, (int)((5LL * c->num_sms * 2) / std::max(1, gx * gy))));
+    // z-chunks: ~7 CTAs fit an SM (30 KB of shared memory each); pick the chunk count that minimises waves x (planes per chunk + 2)
+    const long long cap = 7LL * c->num_sms, tiles = (long long)gx * gy;
+    int nch = 1;
+    {
+        double best = 1e300;
+        for (int k = 1; k <= 16 && k <= std::max(1, nz / 4); k++) {
+            const int zc = div_up(nz, k), kk = div_up(nz, zc);
+            const double cost = ceil((double)(tiles * kk) / cap) * (zc + 2.0);
+            if (cost < best * 0.999) { best = cost; nch = kk; }
+        }
+    }
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
-    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + 2 * T3_Y_BYTES;
+    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + T3_Y_BYTES;
     k_hex8_tc32c<<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
     c->launches++;
     TOB_KERNEL_CHECK();
