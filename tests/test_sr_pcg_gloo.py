@@ -66,21 +66,31 @@ def _worker(rank, world, port, shape, out_q):
         bo = b[kn0 * plane:kn1 * plane]
         bnorm = np.sqrt(allsum(float(bo @ bo))[0])
         # ---- single-reduction iteration (cgsr.cuh): U then S, one all-reduce of three sums -------------------------------
-        xs = np.zeros_like(bo); r = bo.copy(); u = r / dloc; w = apply(u)
+        # as the kernel runs it (cgsr.cu): the inverse diagonal is the fp32 copy, the residual is not stored (u = D^-1 r carries
+        # it: u -= alpha D^-1 s, r = u / dinv inside the sums) and x is updated every other iteration (lazy update)
+        dinv = (1.0 / dloc).astype(np.float32).astype(np.float64)
+        xs = np.zeros_like(bo); u = dinv * bo; w = apply(u)
         p = np.zeros_like(bo); s = np.zeros_like(bo)
-        gam, rr, dlt = allsum(float(r @ u), float(r @ r), float(w @ u))
+        rloc = u / dinv
+        gam, rr, dlt = allsum(float(rloc @ u), float(rloc @ rloc), float(w @ u))
         gam_prev, alpha_prev, first, its_sr, nred_sr = 1.0, 1.0, True, 0, 1
         while np.sqrt(rr) > 1e-8 * bnorm and its_sr < 5000:
-            if first:
-                beta, alpha = 0.0, gam / dlt
-            else:
-                beta = gam / gam_prev
-                alpha = gam / (dlt - beta * gam / alpha_prev)
-            p = u + beta * p; s = w + beta * s; xs += alpha * p; r -= alpha * s; u = r / dloc
-            w = apply(u)
-            gam_prev, alpha_prev, first = gam, alpha, False
-            gam, rr, dlt = allsum(float(r @ u), float(r @ r), float(w @ u))
-            its_sr += 1; nred_sr += 1
+            for xm in (1, 2):  # iterations come in pairs; the even one leaves x alone
+                if first:
+                    beta, alpha = 0.0, gam / dlt
+                else:
+                    beta = gam / gam_prev
+                    alpha = gam / (dlt - beta * gam / alpha_prev)
+                p_old = p
+                p = u + beta * p; s = w + beta * s
+                if xm == 2:
+                    xs += alpha_prev * p_old + alpha * p
+                u = u - alpha * dinv * s
+                w = apply(u)
+                gam_prev, alpha_prev, first = gam, alpha, False
+                rloc = u / dinv
+                gam, rr, dlt = allsum(float(rloc @ u), float(rloc @ rloc), float(w @ u))
+                its_sr += 1; nred_sr += 1
         # ---- classical PCG: two reductions per iteration ---------------------------------------------------------------------
         xc = np.zeros_like(bo); r = bo.copy(); z = r / dloc; p = z.copy()
         (rz,) = allsum(float(r @ z)); its_cl, nred_cl, rr2 = 0, 1, float("inf")

@@ -20,12 +20,17 @@ __device__ __forceinline__ void cg_st_release_sys(unsigned long long* p, unsigne
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// XM: lazy update of the iterate as in vecops.cu -- 1 = even iteration of a pair (x untouched: 9 instead of 11 vector streams),
-// 2 = odd iteration (x += alpha_even p_even + alpha p; p_even is simply the direction this kernel loads), 0 = every iteration
+// XM: lazy update of the iterate as in vecops.cu -- 1 = even iteration of a pair (x untouched), 2 = odd iteration
+// (x += alpha_even p_even + alpha p; p_even is simply the direction this kernel loads), 0 = every iteration.
+// The residual is NOT stored during the iteration: u = D^-1 r carries it (r = u / dinv), so the update is
+//     u -= alpha * dinv * s ;   r.u = sum u^2 / dinv ;   r.r = sum (u / dinv)^2
+// and an iteration streams u, w, p, s, dinv(fp32) in and p, s, u out (+ x in/out every other iteration): 7.5 / 9.5 vector
+// streams instead of 10 / 12 (device time stamps on 2 GPUs: this kernel was 52 us of an 86 us iteration).
+// Set-up (MODE 0) reads the true residual r = b - A x once.
 template <int MODE, int XM>
 __global__ void __launch_bounds__(kFlatThreads)
-k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __restrict__ r, double* __restrict__ u,
-            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s, const double* __restrict__ dinv, long long n,
+k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const double* __restrict__ r, double* __restrict__ u,
+            const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s, const float* __restrict__ dinv, long long n,
             long long plane, double* __restrict__ upart, const __grid_constant__ CgPeers pe, size_t red_off0, size_t red_off1) {
     __shared__ double red[32];
     __shared__ double sh[2];
@@ -34,6 +39,7 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
     if (MODE == 1) {
         if (threadIdx.x == 0) {
             double gam, rr, del;
+            if (blockIdx.x == 0) cg_trace(pe, st.epoch + 1, 0);
             if (pe.n > 1) {
                 // the three sums of every rank were stored into my arena by the last CTA of that rank's SpMV
                 const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pe.arena);
@@ -48,6 +54,7 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
             } else {
                 gam = cg->sums[0]; rr = cg->sums[1]; del = cg->sums[2];
             }
+            if (blockIdx.x == 0) cg_trace(pe, st.epoch + 1, 1);
             double a, b;
             if (st.first != 0.0) { b = 0.0; a = gam / del; }
             else { b = gam / st.gam_prev; a = gam / (del - b * gam / st.alpha_prev); }
@@ -67,18 +74,20 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
     const unsigned long long e = st.epoch + 1;
     const long long n2 = n >> 1, plane2 = plane >> 1;
     double2* x2 = reinterpret_cast<double2*>(x);
-    double2* r2 = reinterpret_cast<double2*>(r);
+    const double2* r2 = reinterpret_cast<const double2*>(r);
     double2* u2 = reinterpret_cast<double2*>(u);
     const double2* w2 = reinterpret_cast<const double2*>(w);
     double2* p2 = reinterpret_cast<double2*>(p);
     double2* s2 = reinterpret_cast<double2*>(s);
-    const double2* d2 = reinterpret_cast<const double2*>(dinv);
+    const float2* d2 = reinterpret_cast<const float2*>(dinv);
     double2* lo2 = reinterpret_cast<double2*>(pe.u_lo_ghost);
     double2* hi2 = reinterpret_cast<double2*>(pe.u_hi_ghost);
     double gam = 0.0, rr = 0.0;
     bool remote = false;  // only the threads that stored into a neighbour need the system-scope fence
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-        double2 rv = r2[i];
+        const float2 df = d2[i];
+        const double dx = (double)df.x, dy = (double)df.y;
+        double2 un;
         if (MODE == 1) {
             const double2 uv = u2[i], wv = w2[i];
             double2 pv = p2[i], sv = s2[i];
@@ -91,24 +100,30 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
                 xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
                 x2[i] = xv;
             }
-            rv.x = fma(-alpha, sv.x, rv.x); rv.y = fma(-alpha, sv.y, rv.y);
-            p2[i] = pv; s2[i] = sv; r2[i] = rv;
+            un.x = fma(-alpha * dx, sv.x, uv.x); un.y = fma(-alpha * dy, sv.y, uv.y);
+            p2[i] = pv; s2[i] = sv;
+        } else {
+            const double2 rv = r2[i];
+            un = make_double2(dx * rv.x, dy * rv.y);
         }
-        const double2 dv = d2[i];
-        const double2 un = make_double2(dv.x * rv.x, dv.y * rv.y);
         u2[i] = un;
         if (lo2 && i < plane2) { lo2[i] = un; remote = true; }                        // my first owned plane = lower neighbour's top ghost
         if (hi2 && i >= n2 - plane2) { hi2[i - (n2 - plane2)] = un; remote = true; }  // my last owned plane = upper neighbour's bottom ghost
-        gam = fma(rv.x, un.x, gam); gam = fma(rv.y, un.y, gam);
-        rr = fma(rv.x, rv.x, rr); rr = fma(rv.y, rv.y, rr);
+        // r = u / dinv (padding entries carry dinv = 0 and u = 0)
+        const double rx = dx != 0.0 ? un.x / dx : 0.0, ry = dy != 0.0 ? un.y / dy : 0.0;
+        gam = fma(rx, un.x, gam); gam = fma(ry, un.y, gam);
+        rr = fma(rx, rx, rr); rr = fma(ry, ry, rr);
     }
-    if (remote) __threadfence_system();
+    // one system-scope fence per block that stored into a neighbour, by thread 0 behind the block barrier (fence cumulativity
+    // covers the other threads' stores) -- a MEMBAR.SYS per warp cost ~10 us of this kernel on 2 GPUs
+    const int any_remote = __syncthreads_or(remote ? 1 : 0);
     gam = block_sum(gam, red);
     rr = block_sum(rr, red);
     if (threadIdx.x == 0) {
         upart[blockIdx.x] = gam;
         upart[gridDim.x + blockIdx.x] = rr;
         if (pe.n > 1) {
+            if (any_remote) __threadfence_system();
             __threadfence();
             const unsigned int done = atomicAdd(&cg->ucounter, 1u) + 1u;
             if (done == gridDim.x) {  // every block of this launch has pushed its share of the boundary planes
@@ -116,13 +131,14 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, double* __r
                 __threadfence_system();
                 if (pe.rank > 0) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank - 1]) + F_CG_FROM_HI, e);
                 if (pe.rank < pe.n - 1) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank + 1]) + F_CG_FROM_LO, e);
+                cg_trace(pe, e, 2);
             }
         }
     }
 }
 
-int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, double* r, double* u, const double* w,
-              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode) {
+int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, const double* r, double* u, const double* w,
+              double* p, double* s, const float* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode) {
     const int nb = flat_grid(c, g.own_len);
     const long long o = g.own_off;
     const size_t r0 = peers.n > 1 ? cg_red_off(peers.n, 0, 0) : 0, r1 = peers.n > 1 ? cg_red_off(peers.n, 1, 0) : 0;

@@ -6,6 +6,7 @@
 // iteration are available after ONE operator application:
 //     U:  [alpha, beta from last iteration's sums]   p = u + beta p ;  s = w + beta s ;  x += alpha p ;  r -= alpha s ;
 //         u = D^-1 r  (also stored straight into the neighbours' ghost planes over NVLink) ;  partials of r.u and r.r
+//         (r itself is not stored: u -= alpha D^-1 s and r = D u where the sums need it -- two vector streams fewer)
 //     S:  w = A u  (z-march SpMV; only the CTAs that touch a ghost plane wait for the neighbour's flag) ; partials of w.u ;
 //         the LAST CTA to finish sums all partials, stores the three sums into every peer's arena and raises a flag.
 // The next U spins on the peers' flags and adds the per-rank sums in rank order (bitwise identical on all ranks).
@@ -37,7 +38,18 @@ struct CgPeers {  // per-launch description of the neighbourhood (by value in th
     unsigned char* peer[kMaxRanks] = {};    // every rank's arena
     double* u_lo_ghost = nullptr;           // lower neighbour's TOP ghost plane of u (null if none)
     double* u_hi_ghost = nullptr;           // upper neighbour's BOTTOM ghost plane of u
+    // TOB_CG_TRACE=1: %globaltimer stamps, 8 per epoch (slot = epoch % trace_cap):
+    //   0 U entry, 1 U sums arrived, 2 U last block done (flags raised), 3 S entry, 4 S ghost planes arrived, 5 S last CTA published
+    unsigned long long* trace = nullptr;
+    int trace_cap = 0;
 };
+__device__ __forceinline__ void cg_trace(const CgPeers& pe, unsigned long long epoch, int k) {
+    if (pe.trace) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        pe.trace[(epoch % (unsigned long long)pe.trace_cap) * 8 + k] = t;
+    }
+}
 
 size_t cg_red_off(int n, int parity, int rank);  // byte offset of a reduction slot inside an arena (comm.cu)
 
@@ -51,7 +63,8 @@ int peer_vec_alloc(tob_ctx_impl* c, size_t nbytes, PeerVec* out);
 void peer_vec_free(tob_ctx_impl* c, PeerVec* v);
 
 // U kernel.  mode 0 = set-up (u = dinv r only, first = 1), mode 1 = iteration.  par = parity of the state it reads.
-int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, double* r, double* u, const double* w,
-              double* p, double* s, const double* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode = 0);
+// r is read by the set-up launch only (the iteration carries the residual in u = D^-1 r); dinv is the fp32 copy of the inverse diagonal
+int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, const double* r, double* u, const double* w,
+              double* p, double* s, const float* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode = 0);
 
 }  // namespace tob

@@ -106,6 +106,11 @@ static int sr_setup(tob_elast_impl* h) {
     CgPeers& pe = h->sr_pe;
     pe = CgPeers();
     pe.n = c->desc.nranks; pe.rank = c->desc.rank;
+    if (getenv("TOB_CG_TRACE") && atoi(getenv("TOB_CG_TRACE"))) {  // diagnostic: device time stamps of the U/S pairs (cgsr.cuh)
+        pe.trace_cap = 4096;
+        TOB_CUDA(cudaMalloc(&pe.trace, sizeof(unsigned long long) * 8 * pe.trace_cap));
+        TOB_CUDA(cudaMemsetAsync(pe.trace, 0, sizeof(unsigned long long) * 8 * pe.trace_cap, c->stream));
+    }
     if (pe.n > 1) {
         pe.arena = c->peer.arena;
         for (int k = 0; k < pe.n; k++) pe.peer[k] = c->peer.peer[k];
@@ -130,6 +135,7 @@ static void sr_destroy(tob_elast_impl* h) {
     peer_vec_free(h->c, &h->sr_u);
     cudaFree(h->sr_cg); h->sr_cg = nullptr;
     cudaFree(h->sr_upart); h->sr_upart = nullptr;
+    if (h->sr_pe.trace) { cudaFree(h->sr_pe.trace); h->sr_pe.trace = nullptr; }
 }
 
 // R holds b - A U on entry; iterates until ||r|| <= tol.  *it / *rnorm as in elast_pcg.
@@ -145,14 +151,14 @@ static int elast_pcg_sr(tob_elast_impl* h, double tol, double bnorm, int* it_out
     TOB_CHECK(vec_zero(c, h->Z, g.nvec));
     int np = 0;
     // set-up pair: u = D^-1 r (+ halo), w = A u, sums
-    TOB_CHECK(cg_update(c, g, h->sr_cg, 0, 0, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV, h->sr_upart, &h->sr_nbU, h->sr_pe));
+    TOB_CHECK(cg_update(c, g, h->sr_cg, 0, 0, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV32, h->sr_upart, &h->sr_nbU, h->sr_pe));
     c->cg_epoch++;
     h->sr_par = 1;
     TOB_CHECK(elast_apply(h, u, h->Q, EPI_CGDOT, false, 0, nullptr, &np));
     int par = 1, it = 0;
     static const bool lazyx = !(getenv("TOB_PCG_LAZYX") && atoi(getenv("TOB_PCG_LAZYX")) == 0);
     auto one_iteration = [&](int xm) -> int {  // xm: 1 = even, 2 = odd iteration of a pair (lazy x update, cgsr.cu)
-        TOB_CHECK(cg_update(c, g, h->sr_cg, par, 1, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV, h->sr_upart, &h->sr_nbU, h->sr_pe, lazyx ? xm : 0));
+        TOB_CHECK(cg_update(c, g, h->sr_cg, par, 1, h->U, h->R, u, h->Q, h->P, h->Z, h->DINV32, h->sr_upart, &h->sr_nbU, h->sr_pe, lazyx ? xm : 0));
         c->cg_epoch++;
         par ^= 1;
         h->sr_par = par;
@@ -208,6 +214,29 @@ static int elast_pcg_sr(tob_elast_impl* h, double tol, double bnorm, int* it_out
     h->prof_stride = stride_saved;
     *it_out = it;
     *rnorm_out = rnorm;
+    if (h->sr_pe.trace) {  // TOB_CG_TRACE: mean phase durations over the epochs still in the ring
+        const int cap = h->sr_pe.trace_cap;
+        std::vector<unsigned long long> t((size_t)cap * 8);
+        TOB_CUDA(cudaMemcpy(t.data(), h->sr_pe.trace, t.size() * 8, cudaMemcpyDeviceToHost));
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        long long cnt = 0;
+        const unsigned long long e1 = c->cg_epoch;
+        for (unsigned long long e = (e1 > (unsigned long long)cap ? e1 - cap + 2 : 2); e + 1 < e1; e++) {
+            const unsigned long long* a = &t[(e % cap) * 8];
+            const unsigned long long* b = &t[((e + 1) % cap) * 8];
+            if (!a[0] || !a[5] || !b[0] || a[5] < a[0] || b[0] < a[5]) continue;
+            acc[0] += (double)(a[1] - a[0]);                     // U: wait for the sums
+            acc[1] += (double)((a[2] ? a[2] : a[3]) - a[1]);     // U: body (to the last block / next entry on one rank)
+            acc[2] += (double)(a[3] - (a[2] ? a[2] : a[3]));     // gap U -> S
+            acc[3] += (double)(a[4] ? a[4] - a[3] : 0);          // S: wait for the ghost planes
+            acc[4] += (double)(a[5] - (a[4] ? a[4] : a[3]));     // S: body + reduction
+            acc[5] += (double)(b[0] - a[5]);                     // gap S -> next U
+            cnt++;
+        }
+        if (cnt)
+            fprintf(stderr, "[tob cg trace] rank %d: %lld iterations  U-wait %.2f  U-body %.2f  gap %.2f  S-wait %.2f  S-body %.2f  gap %.2f  (us, mean)\n",
+                    c->desc.rank, cnt, acc[0] / cnt * 1e-3, acc[1] / cnt * 1e-3, acc[2] / cnt * 1e-3, acc[3] / cnt * 1e-3, acc[4] / cnt * 1e-3, acc[5] / cnt * 1e-3);
+    }
     return 0;
 }
 

@@ -576,11 +576,14 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 // chunks that read a ghost plane wait (system-scope acquire of the epoch flag in my arena)
                 const unsigned long long e = P.cg->st[P.cgpar].epoch;
                 const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(P.pe.arena);
+                const bool tr = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == (P.pe.rank > 0 ? 0 : gridDim.z - 1));
+                if (tr) cg_trace(P.pe, e, 3);
                 const long long t0 = clock64();  // bounded: a dead neighbour must not hang this GPU (the solve then fails its residual check)
                 if (z0 == P.zout0 && P.pe.rank > 0)
                     while (ld_acquire_sys_u64(&flags[F_CG_FROM_LO]) < e && clock64() - t0 < 8000000000LL) {}
                 if (z1 == P.zout1 && P.pe.rank < P.pe.n - 1)
                     while (ld_acquire_sys_u64(&flags[F_CG_FROM_HI]) < e && clock64() - t0 < 8000000000LL) {}
+                if (tr) cg_trace(P.pe, e, 4);
             }
             for (int s = 0; s < L::STAGES; s++) mbar_init(&bars[s], 1);
             for (int s = 0; s < L::STAGES; s++) mbar_init(&ebars[s], nactive);
@@ -829,6 +832,7 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                     __threadfence_system();
                     st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.pe.peer[tid]) + F_CG_RED0 + P.pe.rank, e);
                 }
+                if (tid == 0) cg_trace(P.pe, e, 5);
             }
         }
     }

@@ -544,15 +544,20 @@ constexpr int T3_SLOT = ((T3_PX * T3_PY * 16 + 127) / 128) * 128;
 constexpr int T3_B_BYTES = 4 * 1024;               // 4 K-steps x (2 chunks x 32 rows x 16 B)
 constexpr int T3_Y_BYTES = 8 * 128 * 16;           // one transposed output buffer: [local node (8)][element (128)] float4
 
+// Y3: the transposed buffer holds three float planes per local node ([24][128] floats, 12 KB, conflict-free 32-bit accesses: 8 CTAs
+// per SM) instead of one float4 ([8][128], 16 KB, a quarter of the wavefronts carry the padding lane: 7 CTAs per SM)
+template <bool Y3>
 __global__ void __launch_bounds__(128)
 k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc2Params P) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];  // (no swizzle: the operand descriptors need 16-byte alignment only)
     unsigned char* sB = smem;
     unsigned char* sP = smem + T3_B_BYTES;                     // 4 plane slots
-    float4* sY = reinterpret_cast<float4*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // [8][128] (one buffer: occupancy beats the saved barrier)
-    __shared__ __align__(8) uint64_t full[4];
-    __shared__ __align__(8) uint64_t mma_done[2];  // one per TMEM accumulator (the MMAs run one layer ahead of the epilogue)
-    __shared__ uint32_t tmem_base_s;
+    float4* sY = reinterpret_cast<float4*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // transposed outputs (one buffer: occupancy beats the saved barrier)
+    // barriers and the TMEM slot live behind the buffers (static shared memory would round the CTA up by 2 KB: 7 instead of 8 per SM)
+    unsigned char* tail = smem + T3_B_BYTES + 4 * T3_SLOT + (Y3 ? T3_Y_BYTES * 3 / 4 : T3_Y_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [4]
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(tail + 32); // [2]: one per TMEM accumulator (the MMAs run one layer ahead of the epilogue)
+    uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(tail + 48);
 
     const int t = threadIdx.x, warp = t >> 5;
     const int ix = t & (T3_EX - 1), iy = t >> 3;
@@ -637,8 +642,15 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int n = 0; n < 8; n++)  // D columns are laid out [local node][4] (the operand blocks pad every node to 4 rows)
-                Yb[n * 128 + t] = make_float4(Ee * __uint_as_float(d[4 * n]), Ee * __uint_as_float(d[4 * n + 1]), Ee * __uint_as_float(d[4 * n + 2]), 0.0f);
+            for (int n = 0; n < 8; n++) {  // D columns are laid out [local node][4] (the operand blocks pad every node to 4 rows)
+                if (Y3) {
+                    float* Yf = reinterpret_cast<float*>(sY);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) Yf[(3 * n + c) * 128 + t] = Ee * __uint_as_float(d[4 * n + c]);
+                } else {
+                    Yb[n * 128 + t] = make_float4(Ee * __uint_as_float(d[4 * n]), Ee * __uint_as_float(d[4 * n + 1]), Ee * __uint_as_float(d[4 * n + 2]), 0.0f);
+                }
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // Yb complete; TMEM free; everybody is past the epilogue of layer L - 1 (slot of plane L - 1 free)
@@ -651,9 +663,18 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
                 const int a = q & 1, b = q >> 1;
                 const int e = t - (8 * b + a);
                 const int nlo = b ? (a ? 2 : 3) : (a ? 1 : 0);  // reference local node (a, b, 0); (a, b, 1) = nlo + 4
-                const float4 vl = Yb[nlo * 128 + e], vu = Yb[(nlo + 4) * 128 + e];
-                low[0] += vl.x; low[1] += vl.y; low[2] += vl.z;
-                up[0] += vu.x; up[1] += vu.y; up[2] += vu.z;
+                if (Y3) {
+                    const float* Yf = reinterpret_cast<const float*>(sY);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        low[c] += Yf[(3 * nlo + c) * 128 + e];
+                        up[c] += Yf[(3 * (nlo + 4) + c) * 128 + e];
+                    }
+                } else {
+                    const float4 vl = Yb[nlo * 128 + e], vu = Yb[(nlo + 4) * 128 + e];
+                    low[0] += vl.x; low[1] += vl.y; low[2] += vl.z;
+                    up[0] += vu.x; up[1] += vu.y; up[2] += vu.z;
+                }
             }
         }
         if (L >= z0 && node_out) {
@@ -715,7 +736,8 @@ int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     const int gx = div_up(g.nxn, T3_EX - 1), gy = div_up(g.nyn, T3_EY - 1);
     const int nz = P.zout1 - P.zout0;
     // z-chunks: ~7 CTAs fit an SM (30 KB of shared memory each); pick the chunk count that minimises waves x (planes per chunk + 2)
-    const long long cap = 7LL * c->num_sms, tiles = (long long)gx * gy;
+    static const bool y3 = !(getenv("TOB_TC32_Y3") && atoi(getenv("TOB_TC32_Y3")) == 0);
+    const long long cap = (y3 ? 8LL : 7LL) * c->num_sms, tiles = (long long)gx * gy;
     int nch = 1;
     {
         double best = 1e300;
@@ -727,8 +749,15 @@ int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     }
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
-    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + T3_Y_BYTES;
-    k_hex8_tc32c<<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + (y3 ? T3_Y_BYTES * 3 / 4 : T3_Y_BYTES) + 64;
+    static bool carve[64] = {};
+    if (c->device >= 0 && c->device < 64 && !carve[c->device]) {  // 8 x 27 KB only fit with the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_hex8_tc32c<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_hex8_tc32c<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve[c->device] = true;
+    }
+    if (y3) k_hex8_tc32c<true><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    else k_hex8_tc32c<false><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;
