@@ -28,7 +28,7 @@ __device__ __forceinline__ void cg_st_release_sys(unsigned long long* p, unsigne
 // streams instead of 10 / 12 (device time stamps on 2 GPUs: this kernel was 52 us of an 86 us iteration).
 // Set-up (MODE 0) reads the true residual r = b - A x once.
 template <int MODE, int XM>
-__global__ void __launch_bounds__(kFlatThreads)
+__global__ void __launch_bounds__(kFlatThreads, 4)  // 64 registers: 4 blocks per SM (the unconstrained build took 106 -> 2 blocks, 4 waves)
 k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const double* __restrict__ r, double* __restrict__ u,
             const double* __restrict__ w, double* __restrict__ p, double* __restrict__ s, const float* __restrict__ dinv, long long n,
             long long plane, double* __restrict__ upart, const __grid_constant__ CgPeers pe, size_t red_off0, size_t red_off1) {
@@ -83,8 +83,7 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const doubl
     double2* lo2 = reinterpret_cast<double2*>(pe.u_lo_ghost);
     double2* hi2 = reinterpret_cast<double2*>(pe.u_hi_ghost);
     double gam = 0.0, rr = 0.0;
-    bool remote = false;  // only the threads that stored into a neighbour need the system-scope fence
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    auto item = [&](const long long i) {
         const float2 df = d2[i];
         const double dx = (double)df.x, dy = (double)df.y;
         double2 un;
@@ -107,39 +106,55 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const doubl
             un = make_double2(dx * rv.x, dy * rv.y);
         }
         u2[i] = un;
-        if (lo2 && i < plane2) { lo2[i] = un; remote = true; }                        // my first owned plane = lower neighbour's top ghost
-        if (hi2 && i >= n2 - plane2) { hi2[i - (n2 - plane2)] = un; remote = true; }  // my last owned plane = upper neighbour's bottom ghost
+        if (lo2 && i < plane2) lo2[i] = un;                        // my first owned plane = lower neighbour's top ghost
+        if (hi2 && i >= n2 - plane2) hi2[i - (n2 - plane2)] = un;  // my last owned plane = upper neighbour's bottom ghost
         // r = u / dinv (padding entries carry dinv = 0 and u = 0)
         const double rx = dx != 0.0 ? un.x / dx : 0.0, ry = dy != 0.0 ? un.y / dy : 0.0;
         gam = fma(rx, un.x, gam); gam = fma(ry, un.y, gam);
         rr = fma(rx, rx, rr); rr = fma(ry, ry, rr);
+    };
+    // Phase A: the two boundary planes first, by the first nbnd blocks -- their stores into the neighbours' ghost planes are
+    // fenced and the neighbours' flags raised while the rest of the vector is still being streamed (the flag used to leave at
+    // the very end of the kernel, behind a system fence: ~4 us per neighbour on the critical path of every iteration)
+    const long long nA = min(2 * plane2, n2);
+    const int nbnd = (int)min((long long)gridDim.x, (nA + blockDim.x - 1) / blockDim.x);
+    if ((int)blockIdx.x < nbnd) {
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nA; j += (long long)nbnd * blockDim.x)
+            item(j < plane2 ? j : n2 - nA + j);
+        if (pe.n > 1 || pe.trace) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();  // one fence per block, behind the barrier (cumulative over the block's stores)
+                const unsigned int done = atomicAdd(&cg->ucounter, 1u) + 1u;
+                if (done == (unsigned int)nbnd) {
+                    cg->ucounter = 0u;
+                    __threadfence_system();
+                    if (pe.rank > 0) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank - 1]) + F_CG_FROM_HI, e);
+                    if (pe.rank < pe.n - 1) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank + 1]) + F_CG_FROM_LO, e);
+                    cg_trace(pe, e, 2);
+                }
+            }
+        }
     }
-    // one system-scope fence per block that stored into a neighbour, by thread 0 behind the block barrier (fence cumulativity
-    // covers the other threads' stores) -- a MEMBAR.SYS per warp cost ~10 us of this kernel on 2 GPUs
-    const int any_remote = __syncthreads_or(remote ? 1 : 0);
+    // Phase B: the interior, grid-stride, the boundary blocks last in the block order (they already did an item)
+    const long long nI = n2 - nA;
+    const int bo = ((int)blockIdx.x + (int)gridDim.x - nbnd) % (int)gridDim.x;
+    for (long long k = (long long)bo * blockDim.x + threadIdx.x; k < nI; k += (long long)gridDim.x * blockDim.x) item(plane2 + k);
     gam = block_sum(gam, red);
     rr = block_sum(rr, red);
     if (threadIdx.x == 0) {
         upart[blockIdx.x] = gam;
         upart[gridDim.x + blockIdx.x] = rr;
-        if (pe.n > 1) {
-            if (any_remote) __threadfence_system();
-            __threadfence();
-            const unsigned int done = atomicAdd(&cg->ucounter, 1u) + 1u;
-            if (done == gridDim.x) {  // every block of this launch has pushed its share of the boundary planes
-                cg->ucounter = 0u;
-                __threadfence_system();
-                if (pe.rank > 0) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank - 1]) + F_CG_FROM_HI, e);
-                if (pe.rank < pe.n - 1) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank + 1]) + F_CG_FROM_LO, e);
-                cg_trace(pe, e, 2);
-            }
-        }
     }
 }
 
 int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode, double* x, const double* r, double* u, const double* w,
               double* p, double* s, const float* dinv, double* upart, int* nbU, const CgPeers& peers, int xmode) {
-    const int nb = flat_grid(c, g.own_len);
+    // one grid for all variants of a solve (the S kernel's last CTA sums nb partials): a single resident wave
+    int nb = resident_grid(c, (const void*)k_cg_update<1, 0>, kFlatThreads, g.own_len);
+    nb = std::min(nb, resident_grid(c, (const void*)k_cg_update<1, 1>, kFlatThreads, g.own_len));
+    nb = std::min(nb, resident_grid(c, (const void*)k_cg_update<1, 2>, kFlatThreads, g.own_len));
+    nb = std::min(nb, resident_grid(c, (const void*)k_cg_update<0, 0>, kFlatThreads, g.own_len));
     const long long o = g.own_off;
     const size_t r0 = peers.n > 1 ? cg_red_off(peers.n, 0, 0) : 0, r1 = peers.n > 1 ? cg_red_off(peers.n, 1, 0) : 0;
 #define TOB_CG_ARGS cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride, upart, peers, r0, r1

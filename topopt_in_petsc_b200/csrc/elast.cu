@@ -275,7 +275,7 @@ int elast_pcg(tob_elast_impl* h) {
         double* blk_nxt = c->d_partials + (512 << 10);
         int nbx = 0;
         TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->R, h->R, h->DINV32, nullptr, 0, nullptr, blk_cur, &nbx));
-        TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, nullptr, nullptr));
+        TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, nullptr, nullptr, nullptr, nbx));
         const int check = o.check_every > 0 ? o.check_every : 10;
         const bool graphed1 = !getenv("TOB_PCG_NOGRAPH") && check >= 4;
         // iterations run in (even, odd) pairs with the lazy x update of vecops.cu (xm = 1, 2); TOB_PCG_LAZYX=0 switches it off
@@ -284,7 +284,7 @@ int elast_pcg(tob_elast_impl* h) {
         auto one_iteration1 = [&](double* bc, double* bn, int xm) -> int {
             TOB_CHECK(elast_apply(h, h->P, h->Q, EPI_DOT, false, 0, nullptr, &np));
             TOB_CHECK(pcg_update_xr_f(c, g, h->U, h->R, h->P, h->Q, h->DINV32, c->d_partials, np, bc, bn, &nbx, lazyx ? xm : 0, ab));
-            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, bn, bc, ab));
+            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, bn, bc, ab, nbx));
             return 0;
         };
         const int stride_saved1 = h->prof_stride;
@@ -338,7 +338,7 @@ int elast_pcg(tob_elast_impl* h) {
                 if (!(rnorm == rnorm)) TOB_FAIL("PCG produced NaN (bad density field)");
                 if (rnorm <= tol || rnorm > o.dtol * bnorm) break;
             }
-            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, blk_nxt, blk_cur));
+            TOB_CHECK(pcg_update_p_f(c, g, h->P, h->R, h->DINV32, blk_nxt, blk_cur, nullptr, nbx));
             double* t = blk_cur; blk_cur = blk_nxt; blk_nxt = t;
         }
     } else if (rnorm > tol && bnorm > 0) {

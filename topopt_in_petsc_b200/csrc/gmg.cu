@@ -28,6 +28,7 @@ struct GmgLevel {
     Hex8Operator op;
     bool own_op = false;
     double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr, *dinv = nullptr, *E = nullptr;
+    float* dinv32 = nullptr;  // fp32 copy of dinv for the Chebyshev epilogue of the matrix-free levels (level 0: the solver's)
     unsigned char* mask = nullptr;
     bool own_E = false;
     int res = 0;  // resolution index: this level's elements are 2^res fine elements wide
@@ -186,14 +187,38 @@ static int level_apply(tob_elast_impl* h, GmgLevel& L, const SpmvArgs& a0, int* 
     return hex8_spmv(h->c, L.g, L.op, a, nparts);
 }
 
-__global__ void __launch_bounds__(kFlatThreads) k_cheb_first4(float4* __restrict__ x, float4* __restrict__ d, const float4* __restrict__ b,
-                                                              const float4* __restrict__ dinv, float s1, long long n) {
+// first Chebyshev step from a zero iterate, fused with the fp64 -> V4 conversion of the right-hand side (b4 is what the later
+// steps of this V-cycle -- pre- and post-smoothing -- read)
+__global__ void __launch_bounds__(256) k_cheb_first4(float4* __restrict__ x, float4* __restrict__ d, float4* __restrict__ b4,
+                                                     const double* __restrict__ b, const float4* __restrict__ dinv, float s1, int nxn, int nyn,
+                                                     int nzl, int px, long long nstride, long long pstride, long long p4) {
+    const long long n = (long long)nxn * nyn * nzl;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float4 bv = b[i], dv = dinv[i];
+        const int ix = (int)(i % nxn);
+        const long long t = i / nxn;
+        const int iy = (int)(t % nyn), iz = (int)(t / nyn);
+        const long long so = (long long)iz * pstride + (long long)iy * px + ix;
+        const long long o = (long long)iz * p4 + (long long)iy * nxn + ix;
+        const float4 bv = make_float4((float)b[so], (float)b[so + nstride], (float)b[so + 2 * nstride], 0.0f);
+        const float4 dv = dinv[o];
         const float4 v = make_float4(s1 * dv.x * bv.x, s1 * dv.y * bv.y, s1 * dv.z * bv.z, 0.0f);
-        d[i] = v;
-        x[i] = v;
+        b4[o] = bv;
+        d[o] = v;
+        x[o] = v;
     }
+}
+
+static int tf32_buffers(tob_elast_impl* h, GmgLevel& L) {
+    tob_ctx_impl* c = h->c;
+    GmgHierarchy* mg = h->mg;
+    if (mg->xa4) return 0;
+    const long long nn = v4_plane_nodes(L.g) * L.g.nzl();
+    float4** vs[] = {&mg->xa4, &mg->xb4, &mg->b4, &mg->d4, &mg->dinv4};
+    for (auto v : vs) {
+        TOB_CUDA(cudaMalloc(v, sizeof(float4) * nn));
+        TOB_CUDA(cudaMemsetAsync(*v, 0, sizeof(float4) * nn, c->stream));
+    }
+    return 0;
 }
 
 // The same Chebyshev-Jacobi sweep on the finest level in single precision on the tensor cores: every step is ONE launch of
@@ -209,18 +234,12 @@ static int cheb_smooth_tf32(tob_elast_impl* h, GmgLevel& L, int k, bool zero_ini
     LevelGrid g4 = g;
     g4.pstride = 2 * v4_plane_nodes(g);
     g4.nvec = g4.pstride * g.nzl();
-    if (!mg->xa4) {
-        float4** vs[] = {&mg->xa4, &mg->xb4, &mg->b4, &mg->d4, &mg->dinv4};
-        for (auto v : vs) {
-            TOB_CUDA(cudaMalloc(v, sizeof(float4) * nn));
-            TOB_CUDA(cudaMemsetAsync(*v, 0, sizeof(float4) * nn, c->stream));
-        }
-    }
+    TOB_CHECK(tf32_buffers(h, L));
     const double lmax = 1.02 * mg->lam_max, lmin = mg->lam_max / mg->lam_ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
-    TOB_CHECK(vec_st_to_v4(c, g, L.b, mg->b4));
-    TOB_CHECK(vec_st_to_v4(c, g, L.dinv, mg->dinv4));
+    // dinv4 is refreshed with the design (gmg_update); b4 is written by the first (zero-iterate) step of the pre-smoother and is
+    // still the right-hand side when the post-smoother of the same V-cycle runs
     float4 *xin = mg->xa4, *xout = mg->xb4;
     if (!zero_init) TOB_CHECK(vec_st_to_v4(c, g, L.x, xin));
     for (int s = 0; s < k; s++) {
@@ -231,7 +250,8 @@ static int cheb_smooth_tf32(tob_elast_impl* h, GmgLevel& L, int k, bool zero_ini
             s0 = rho_new * rho; s1 = 2.0 * rho_new / delta; rho = rho_new;
         }
         if (s == 0 && zero_init) {
-            k_cheb_first4<<<flat_grid(c, nn), kFlatThreads, 0, c->stream>>>(xin, mg->d4, mg->b4, mg->dinv4, (float)s1, nn);
+            k_cheb_first4<<<flat_grid(c, (long long)g.nxn * g.nyn * g.nzl()), 256, 0, c->stream>>>(
+                xin, mg->d4, mg->b4, L.b, mg->dinv4, (float)s1, g.nxn, g.nyn, g.nzl(), g.px, g.nstride, g.pstride, v4_plane_nodes(g));
             c->launches++;
             TOB_KERNEL_CHECK();
             continue;
@@ -277,7 +297,7 @@ static int cheb_smooth(tob_elast_impl* h, GmgLevel& L, int k, bool zero_init) {
         }
         TOB_CHECK(halo_nodes(c, L.g, xin));
         SpmvArgs a;
-        a.u = xin; a.y = xout; a.epi = EPI_CHEB; a.a0 = L.b; a.a1 = L.dinv; a.o1 = L.d; a.s0 = s0; a.s1 = s1;
+        a.u = xin; a.y = xout; a.epi = EPI_CHEB; a.a0 = L.b; a.a1 = L.dinv; a.a1f = L.dinv32; a.o1 = L.d; a.s0 = s0; a.s1 = s1;
         TOB_CHECK(level_apply(h, L, a, nullptr, s));  // Galerkin levels read their coefficients from the device (step s)
         double* t = xin; xin = xout; xout = t;
     }
@@ -453,10 +473,13 @@ int gmg_update(tob_elast_impl* h) {
     if (!mg) return 0;
     mg->lv[0].E = h->E_st;
     mg->lv[0].dinv = h->DINV;
+    mg->lv[0].dinv32 = h->DINV32;
     mg->lv[0].mask = h->mask;
     if (mg->tf32) {  // the V-cycle is replayed as a CUDA graph: the fp32 copy of the modulus must be refreshed HERE, not inside it
         h->E32_valid = false;
         TOB_CHECK(tc2_prepare(h));
+        TOB_CHECK(tf32_buffers(h, mg->lv[0]));
+        TOB_CHECK(vec_st_to_v4(c, mg->lv[0].g, mg->lv[0].dinv, mg->dinv4));
     }
     for (size_t l = 1; l < mg->lv.size(); l++) {
         GmgLevel &F = mg->lv[l - 1], &C = mg->lv[l];
@@ -465,6 +488,7 @@ int gmg_update(tob_elast_impl* h) {
             // replicated twin of the last distributed level: gather the owned element layers of every rank
             TOB_CHECK(allgatherv_bytes(c, F.E + (long long)(f.ke0 - f.ge0) * f.estride, C.E, mg->ge_off.data(), mg->ge_cnt.data()));
             TOB_CHECK(hex8_diag_inv(c, g, C.op, C.E, C.mask, C.dinv, true));
+            TOB_CHECK(vec_d2f(c, C.dinv, C.dinv32, g.nvec));
             continue;
         }
         if (C.stencil) {  // Galerkin product P^T A P (LinearElasticity.cc:702), redone with every new design (:198-200)
@@ -488,6 +512,7 @@ int gmg_update(tob_elast_impl* h) {
             TOB_CHECK(halo_elems(c, C.E, g.estride, own0, own1, 0, g.nzle() - own1, c->desc.rank > 0 ? 1 : 0, 0));
         }
         TOB_CHECK(hex8_diag_inv(c, g, C.op, C.E, C.mask, C.dinv, true));
+        TOB_CHECK(vec_d2f(c, C.dinv, C.dinv32, g.nvec));
     }
     return 0;
 }
@@ -532,7 +557,7 @@ int gmg_setup(tob_elast_impl* h) {
     GmgLevel& L0 = mg->lv[0];
     L0.g = g0;
     L0.op = h->op;
-    L0.E = h->E_st; L0.dinv = h->DINV; L0.mask = h->mask;
+    L0.E = h->E_st; L0.dinv = h->DINV; L0.dinv32 = h->DINV32; L0.mask = h->mask;
     for (int l = 0; l < nl; l++) {
         GmgLevel& L = mg->lv[l];
         if (l > 0) {
@@ -553,6 +578,8 @@ int gmg_setup(tob_elast_impl* h) {
             L.own_op = true;
             TOB_CHECK(galloc(c, &L.E, L.g.evec));
             TOB_CHECK(galloc(c, &L.dinv, L.g.nvec));
+            TOB_CUDA(cudaMalloc(&L.dinv32, sizeof(float) * L.g.nvec));
+            TOB_CUDA(cudaMemsetAsync(L.dinv32, 0, sizeof(float) * L.g.nvec, c->stream));
             TOB_CUDA(cudaMalloc(&L.mask, (size_t)L.g.mstride * L.g.nzl()));
             TOB_CUDA(cudaMemsetAsync(L.mask, 0, (size_t)L.g.mstride * L.g.nzl(), c->stream));
             L.own_E = true;
@@ -627,7 +654,7 @@ void gmg_destroy(tob_elast_impl* h) {
         GmgLevel& L = mg->lv[l];
         double* vs[] = {L.x, L.x2, L.b, L.r, L.d};
         for (auto v : vs) cudaFree(v);
-        if (L.own_E) { cudaFree(L.E); cudaFree(L.dinv); cudaFree(L.mask); }
+        if (L.own_E) { cudaFree(L.E); cudaFree(L.dinv); cudaFree(L.dinv32); cudaFree(L.mask); }
         if (L.stencil) stencil_free(L.S);
         if (L.own_op) hex8_free_operator(L.op);
     }

@@ -186,6 +186,7 @@ struct ZmParams {
     double* y;
     const double* a0;
     const double* a1;
+    const float* a1f;
     double* o1;
     double s0, s1;
     double* partials;
@@ -475,7 +476,7 @@ k_hex8_zmarch(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ C
                         part = fma(r, r, part);
                     } else {  // EPI_CHEB
                         const double r = P.a0[idx] - au;
-                        const double dn = P.s0 * P.o1[idx] + P.s1 * P.a1[idx] * r;
+                        const double dn = P.s0 * P.o1[idx] + P.s1 * (double)P.a1f[idx] * r;
                         P.o1[idx] = dn;
                         P.y[idx] = uo[c] + dn;
                     }
@@ -571,7 +572,7 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
 
     if (z0 < z1) {
         if (tid == 0) {
-            if (EPI == EPI_CGDOT && P.pe.n > 1) {
+            if (EPI == EPI_CGDOT && (P.pe.n > 1 || P.pe.trace)) {
                 // the boundary planes of the operand are stored into my ghost planes by the neighbours' U kernels: only the
                 // chunks that read a ghost plane wait (system-scope acquire of the epoch flag in my arena)
                 const unsigned long long e = P.cg->st[P.cgpar].epoch;
@@ -766,7 +767,7 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                         } else {  // EPI_CHEB
                             const long long idx = (yp - P.y) + c * P.nstride;
                             const double r = P.a0[idx] - au;
-                            const double dn = P.s0 * P.o1[idx] + P.s1 * P.a1[idx] * r;
+                            const double dn = P.s0 * P.o1[idx] + P.s1 * (double)P.a1f[idx] * r;
                             P.o1[idx] = dn;
                             yp[c * P.nstride] = uo[c] + dn;
                         }
@@ -823,6 +824,7 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
             __syncthreads();
             if (P.pe.n == 1) {
                 if (tid < 3) P.cg->sums[tid] = s_sum[tid];
+                if (tid == 0) cg_trace(P.pe, P.cg->st[P.cgpar].epoch, 5);
             } else {
                 const unsigned long long e = P.cg->st[P.cgpar].epoch;
                 const size_t off = ((e & 1) ? P.red_off1 : P.red_off0) + (size_t)P.pe.rank * 128 * 8;
@@ -861,7 +863,7 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
     ZmParams P;
     P.nxn = g.nxn; P.nyn = g.nyn; P.nzl = g.nzl(); P.px = g.px; P.pm = g.pm; P.mstride = g.mstride; P.mask = a.mask; P.nstride = g.nstride; P.pstride = g.pstride;
     P.zout0 = g.zl_own0(); P.zout1 = g.zl_own1();
-    P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
+    P.y = a.y; P.a0 = a.a0; P.a1 = a.a1; P.a1f = a.a1f; P.o1 = a.o1; P.s0 = a.s0; P.s1 = a.s1; P.partials = c->d_partials;
     P.l2hint = a.l2hint;
     P.cg = a.cg; P.cgpar = a.cgpar; P.upart = a.upart; P.nbU = a.nbU;
     if (a.pe) P.pe = *a.pe; else P.pe = CgPeers();

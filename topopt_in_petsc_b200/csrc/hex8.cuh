@@ -40,7 +40,8 @@ struct SpmvArgs {
     int kernel = SPMV_AUTO;
     // epilogue operands (stored layout)
     const double* a0 = nullptr;          // RESID/CHEB: b
-    const double* a1 = nullptr;          // CHEB: dinv
+    const double* a1 = nullptr;          // (unused by the z-march kernels)
+    const float* a1f = nullptr;          // CHEB: dinv, fp32 copy (the smoother is a preconditioner: half a vector stream less per step)
     double* o1 = nullptr;                // CHEB: d (in/out)
     double s0 = 0, s1 = 0;               // CHEB: d = s0*d + s1*dinv*(b - A u); y = u + d
     int l2hint = 0;                      // L2 eviction hints for the TMA loads (Jacobi-PCG; tob_ctx_impl::l2hint)

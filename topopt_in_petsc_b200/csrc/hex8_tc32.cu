@@ -543,10 +543,14 @@ constexpr int T3_PX = T3_EX + 1, T3_PY = T3_EY + 1;
 constexpr int T3_SLOT = ((T3_PX * T3_PY * 16 + 127) / 128) * 128;
 constexpr int T3_B_BYTES = 4 * 1024;               // 4 K-steps x (2 chunks x 32 rows x 16 B)
 constexpr int T3_Y_BYTES = 8 * 128 * 16;           // one transposed output buffer: [local node (8)][element (128)] float4
+constexpr int T3_X_BYTES = 2 * 4 * 6 * 8 * 4;      // YM 2: [buffer][warp][6 values][8 lanes] floats crossing a warp boundary
 
 // Y3: the transposed buffer holds three float planes per local node ([24][128] floats, 12 KB, conflict-free 32-bit accesses: 8 CTAs
 // per SM) instead of one float4 ([8][128], 16 KB, a quarter of the wavefronts carry the padding lane: 7 CTAs per SM)
-template <bool Y3>
+// YM 2: no transposed buffer at all -- the node sums are formed with warp shuffles (x neighbour = lane - 1, y neighbour = lane - 8);
+// only the row that crosses a warp boundary (6 floats of 8 lanes per warp) goes through shared memory, double-buffered, so a layer
+// needs ONE block barrier and 18 shuffles + 12 quarter-warp shared accesses per warp instead of 48 full-warp shared accesses
+template <int YM>
 __global__ void __launch_bounds__(128)
 k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc2Params P) {
     extern __shared__ __align__(128) unsigned char smem[];  // (no swizzle: the operand descriptors need 16-byte alignment only)
@@ -554,7 +558,8 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
     unsigned char* sP = smem + T3_B_BYTES;                     // 4 plane slots
     float4* sY = reinterpret_cast<float4*>(smem + T3_B_BYTES + 4 * T3_SLOT);  // transposed outputs (one buffer: occupancy beats the saved barrier)
     // barriers and the TMEM slot live behind the buffers (static shared memory would round the CTA up by 2 KB: 7 instead of 8 per SM)
-    unsigned char* tail = smem + T3_B_BYTES + 4 * T3_SLOT + (Y3 ? T3_Y_BYTES * 3 / 4 : T3_Y_BYTES);
+    constexpr bool Y3 = (YM == 1);
+    unsigned char* tail = smem + T3_B_BYTES + 4 * T3_SLOT + (YM == 2 ? T3_X_BYTES : YM == 1 ? T3_Y_BYTES * 3 / 4 : T3_Y_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [4]
     uint64_t* mma_done = reinterpret_cast<uint64_t*>(tail + 32); // [2]: one per TMEM accumulator (the MMAs run one layer ahead of the epilogue)
     uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(tail + 48);
@@ -628,6 +633,7 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         mbar_wait(&mma_done[buf], (uint32_t)(((L - pfirst) >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float4* Yb = sY;
+        float low[3] = {0.0f, 0.0f, 0.0f}, up[3] = {0.0f, 0.0f, 0.0f};
         {
             uint32_t d[32];
             const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(32 * buf);
@@ -641,39 +647,72 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
                   "=r"(d[28]), "=r"(d[29]), "=r"(d[30]), "=r"(d[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (YM == 2) {
+                // D columns are [local node][4]; local node (a, b, g) = g * 4 + (b ? (a ? 2 : 3) : (a ? 1 : 0))
+                const int lane = t & 31;
+                float* X = reinterpret_cast<float*>(sY) + ((L - pfirst) & 1) * (4 * 6 * 8);
+                float a1[6];
 #pragma unroll
-            for (int n = 0; n < 8; n++) {  // D columns are laid out [local node][4] (the operand blocks pad every node to 4 rows)
-                if (Y3) {
-                    float* Yf = reinterpret_cast<float*>(sY);
+                for (int g = 0; g < 2; g++)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) Yf[(3 * n + c) * 128 + t] = Ee * __uint_as_float(d[4 * n + c]);
-                } else {
-                    Yb[n * 128 + t] = make_float4(Ee * __uint_as_float(d[4 * n]), Ee * __uint_as_float(d[4 * n + 1]), Ee * __uint_as_float(d[4 * n + 2]), 0.0f);
+                    for (int c = 0; c < 3; c++) {
+                        // x direction: my element's (0, b) node + the (1, b) node of the element to the left (lane - 1)
+                        const float v00 = Ee * __uint_as_float(d[4 * (4 * g + 0) + c]), v10 = Ee * __uint_as_float(d[4 * (4 * g + 1) + c]);
+                        const float v01 = Ee * __uint_as_float(d[4 * (4 * g + 3) + c]), v11 = Ee * __uint_as_float(d[4 * (4 * g + 2) + c]);
+                        const float a0 = v00 + __shfl_up_sync(0xffffffffu, v10, 1);
+                        a1[3 * g + c] = v01 + __shfl_up_sync(0xffffffffu, v11, 1);
+                        if (g == 0) low[c] = a0; else up[c] = a0;
+                    }
+                if (lane >= 24 && warp < 3) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) X[(warp * 6 + q) * 8 + (lane - 24)] = a1[q];
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();  // crossing rows stored; TMEM free; everybody is past the epilogue of layer L - 1 (slot of plane L - 1 free)
+                if (t == 0 && L + 3 <= z1 && L + 3 > pfirst + 3) issue_plane(L + 3);
+#pragma unroll
+                for (int q = 0; q < 6; q++) {
+                    // y direction: the (., 1) sums of the element row below (lane - 8, or the previous warp's last row)
+                    float bsum = __shfl_up_sync(0xffffffffu, a1[q], 8);
+                    if (lane < 8) bsum = warp > 0 ? X[((warp - 1) * 6 + q) * 8 + lane] : 0.0f;
+                    if (q < 3) low[q] += bsum; else up[q - 3] += bsum;
+                }
+            } else {
+#pragma unroll
+                for (int n = 0; n < 8; n++) {  // D columns are laid out [local node][4] (the operand blocks pad every node to 4 rows)
+                    if (Y3) {
+                        float* Yf = reinterpret_cast<float*>(sY);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) Yf[(3 * n + c) * 128 + t] = Ee * __uint_as_float(d[4 * n + c]);
+                    } else {
+                        Yb[n * 128 + t] = make_float4(Ee * __uint_as_float(d[4 * n]), Ee * __uint_as_float(d[4 * n + 1]), Ee * __uint_as_float(d[4 * n + 2]), 0.0f);
+                    }
                 }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // Yb complete; TMEM free; everybody is past the epilogue of layer L - 1 (slot of plane L - 1 free)
-        if (t == 0 && L + 3 <= z1 && L + 3 > pfirst + 3) issue_plane(L + 3);
-        // ---- node sums: plane L gets `carry` (from layer L - 1) + the lower-node outputs of layer L -------------------------------
-        float low[3] = {0.0f, 0.0f, 0.0f}, up[3] = {0.0f, 0.0f, 0.0f};
-        if (ix >= 1 && iy >= 1) {
+        if (YM != 2) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();  // Yb complete; TMEM free; everybody is past the epilogue of layer L - 1 (slot of plane L - 1 free)
+            if (t == 0 && L + 3 <= z1 && L + 3 > pfirst + 3) issue_plane(L + 3);
+            // ---- node sums: plane L gets `carry` (from layer L - 1) + the lower-node outputs of layer L ---------------------------
+            if (ix >= 1 && iy >= 1) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int a = q & 1, b = q >> 1;
-                const int e = t - (8 * b + a);
-                const int nlo = b ? (a ? 2 : 3) : (a ? 1 : 0);  // reference local node (a, b, 0); (a, b, 1) = nlo + 4
-                if (Y3) {
-                    const float* Yf = reinterpret_cast<const float*>(sY);
+                for (int q = 0; q < 4; q++) {
+                    const int a = q & 1, b = q >> 1;
+                    const int e = t - (8 * b + a);
+                    const int nlo = b ? (a ? 2 : 3) : (a ? 1 : 0);  // reference local node (a, b, 0); (a, b, 1) = nlo + 4
+                    if (Y3) {
+                        const float* Yf = reinterpret_cast<const float*>(sY);
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        low[c] += Yf[(3 * nlo + c) * 128 + e];
-                        up[c] += Yf[(3 * (nlo + 4) + c) * 128 + e];
+                        for (int c = 0; c < 3; c++) {
+                            low[c] += Yf[(3 * nlo + c) * 128 + e];
+                            up[c] += Yf[(3 * (nlo + 4) + c) * 128 + e];
+                        }
+                    } else {
+                        const float4 vl = Yb[nlo * 128 + e], vu = Yb[(nlo + 4) * 128 + e];
+                        low[0] += vl.x; low[1] += vl.y; low[2] += vl.z;
+                        up[0] += vu.x; up[1] += vu.y; up[2] += vu.z;
                     }
-                } else {
-                    const float4 vl = Yb[nlo * 128 + e], vu = Yb[(nlo + 4) * 128 + e];
-                    low[0] += vl.x; low[1] += vl.y; low[2] += vl.z;
-                    up[0] += vu.x; up[1] += vu.y; up[2] += vu.z;
                 }
             }
         }
@@ -699,7 +738,7 @@ k_hex8_tc32c(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ Tc
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) carry[c] = up[c];
-        __syncthreads();  // the node sums are done with the transposed buffer
+        if (YM != 2) __syncthreads();  // the node sums are done with the transposed buffer
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
 }
@@ -736,8 +775,8 @@ int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     const int gx = div_up(g.nxn, T3_EX - 1), gy = div_up(g.nyn, T3_EY - 1);
     const int nz = P.zout1 - P.zout0;
     // z-chunks: ~7 CTAs fit an SM (30 KB of shared memory each); pick the chunk count that minimises waves x (planes per chunk + 2)
-    static const bool y3 = !(getenv("TOB_TC32_Y3") && atoi(getenv("TOB_TC32_Y3")) == 0);
-    const long long cap = (y3 ? 8LL : 7LL) * c->num_sms, tiles = (long long)gx * gy;
+    static const int ym = getenv("TOB_TC32_YM") ? atoi(getenv("TOB_TC32_YM")) : 2;  // 0 float4 buffer, 1 three float planes, 2 shuffles
+    const long long cap = (ym >= 1 ? 8LL : 7LL) * c->num_sms, tiles = (long long)gx * gy;
     int nch = 1;
     {
         double best = 1e300;
@@ -749,15 +788,17 @@ int hex8_tc32c(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
     }
     P.zchunk = div_up(nz, nch);
     nch = div_up(nz, P.zchunk);
-    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + (y3 ? T3_Y_BYTES * 3 / 4 : T3_Y_BYTES) + 64;
+    const int smem_bytes = T3_B_BYTES + 4 * T3_SLOT + (ym == 2 ? T3_X_BYTES : ym == 1 ? T3_Y_BYTES * 3 / 4 : T3_Y_BYTES) + 64;
     static bool carve[64] = {};
     if (c->device >= 0 && c->device < 64 && !carve[c->device]) {  // 8 x 27 KB only fit with the largest shared-memory carve-out
-        cudaFuncSetAttribute(k_hex8_tc32c<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_hex8_tc32c<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_hex8_tc32c<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_hex8_tc32c<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_hex8_tc32c<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         carve[c->device] = true;
     }
-    if (y3) k_hex8_tc32c<true><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
-    else k_hex8_tc32c<false><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    if (ym == 2) k_hex8_tc32c<2><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    else if (ym == 1) k_hex8_tc32c<1><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
+    else k_hex8_tc32c<0><<<dim3(gx, gy, nch), 128, smem_bytes, c->stream>>>(tmX, P);
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;

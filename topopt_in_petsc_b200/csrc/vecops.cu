@@ -4,6 +4,8 @@
 // kernels over the contiguous owned range of the stored layout.
 #include "common.cuh"
 #include "vecops.cuh"
+#include <map>
+#include <mutex>
 
 namespace tob {
 
@@ -157,6 +159,25 @@ int finalize_max(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allredu
 int flat_grid(tob_ctx_impl* c, long long n) {
     long long want = (n + 2 * kFlatThreads - 1) / (2 * kFlatThreads);
     long long cap = (long long)c->num_sms * 8;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+int resident_grid(tob_ctx_impl* c, const void* kernel, int threads, long long n) {
+    static std::mutex mu;
+    static std::map<const void*, int> per_sm;
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = per_sm.find(kernel);
+        if (it == per_sm.end()) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+            per_sm[kernel] = occ;
+        } else occ = it->second;
+    }
+    long long want = (n + 2 * threads - 1) / (2 * threads);
+    const long long cap = (long long)c->num_sms * occ;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     return (int)want;
@@ -417,7 +438,12 @@ k_pcg_update_p_f(double* __restrict__ p, const double* __restrict__ r, const flo
 
 int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, const double* p, const double* q, const float* dinv,
                     const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out, int xmode, double* ab) {
-    const int nb = flat_grid(c, g.own_len);
+    // every launch of the solve uses the same grid (the partial-sum blocks of one launch are read by the next): the occupancy
+    // of the heaviest variant decides
+    int nb = 1 << 30;
+    TOB_L2HINT_SWITCH(c->l2hint, (nb = std::min(nb, resident_grid(c, (const void*)k_pcg_update_xr_f<HM, 0>, kFlatThreads, g.own_len)),
+                                  nb = std::min(nb, resident_grid(c, (const void*)k_pcg_update_xr_f<HM, 1>, kFlatThreads, g.own_len)),
+                                  nb = std::min(nb, resident_grid(c, (const void*)k_pcg_update_xr_f<HM, 2>, kFlatThreads, g.own_len))));
 #define TOB_XR_ARGS x + g.own_off, r + g.own_off, p + g.own_off, q + g.own_off, dinv + g.own_off, g.own_len, pq_parts, n_pq, prev_parts, nb, out_parts, ab
     if (xmode == 1) { TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM, 1><<<nb, kFlatThreads, 0, c->stream>>>(TOB_XR_ARGS))); }
     else if (xmode == 2) { TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_xr_f<HM, 2><<<nb, kFlatThreads, 0, c->stream>>>(TOB_XR_ARGS))); }
@@ -429,10 +455,11 @@ int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, c
     return 0;
 }
 int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const float* dinv, const double* new_parts,
-                   const double* old_parts, double* ab) {
-    const int nb = flat_grid(c, g.own_len);
+                   const double* old_parts, double* ab, int nparts) {
+    int nb = 1;
+    TOB_L2HINT_SWITCH(c->l2hint, (nb = resident_grid(c, (const void*)k_pcg_update_p_f<HM>, kFlatThreads, g.own_len)));
     TOB_L2HINT_SWITCH(c->l2hint, (k_pcg_update_p_f<HM><<<nb, kFlatThreads, 0, c->stream>>>(p + g.own_off, r + g.own_off, dinv + g.own_off,
-                                                                                     g.own_len, new_parts, old_parts, nb, ab)));
+                                                                                     g.own_len, new_parts, old_parts, nparts, ab)));
     c->launches++;
     TOB_KERNEL_CHECK();
     return 0;

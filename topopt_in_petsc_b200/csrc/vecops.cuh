@@ -4,6 +4,9 @@
 namespace tob {
 constexpr int kFlatThreads = 256;
 int flat_grid(tob_ctx_impl* c, long long n);
+// grid of a grid-stride kernel with a per-block prologue (flag waits, partial sums): never more blocks than are resident at once
+// (a second wave would pay the prologue again and run at a fraction of the occupancy); per-kernel occupancy is queried once
+int resident_grid(tob_ctx_impl* c, const void* kernel, int threads, long long n);
 int finalize_sum(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allreduce);
 int finalize_max(tob_ctx_impl* c, int nblocks, int nvals, int slot, bool allreduce);
 int finalize_sum_to(tob_ctx_impl* c, int nblocks, int nvals, double* d_out, bool allreduce);
@@ -21,6 +24,6 @@ int pcg_update_xr_f(tob_ctx_impl* c, const LevelGrid& g, double* x, double* r, c
                     const double* pq_parts, int n_pq, const double* prev_parts, double* out_parts, int* nb_out, int xmode = 0,
                     double* ab = nullptr);
 int pcg_update_p_f(tob_ctx_impl* c, const LevelGrid& g, double* p, const double* r, const float* dinv, const double* new_parts,
-                   const double* old_parts, double* ab = nullptr);
+                   const double* old_parts, double* ab, int nparts);
 int finalize_parts(tob_ctx_impl* c, const double* parts, int nb, int slot);
 }  // namespace tob
