@@ -37,32 +37,40 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const doubl
     const CgState st = cg->st[par];
     double alpha = 0.0, beta = 0.0;
     if (MODE == 1) {
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
             double gam, rr, del;
-            if (blockIdx.x == 0) cg_trace(pe, st.epoch + 1, 0);
+            if (blockIdx.x == 0 && lane == 0) cg_trace(pe, st.epoch + 1, 0);
             if (pe.n > 1) {
-                // the three sums of every rank were stored into my arena by the last CTA of that rank's SpMV
+                // the three sums of every rank were stored into my arena by the last CTA of that rank's SpMV; lane k polls rank k's
+                // flag (system-scope acquire loads cost ~0.6 us each: in sequence they were 5 us on 8 ranks)
                 const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pe.arena);
-                for (int k = 0; k < pe.n; k++)
-                    cg_wait_flag(&flags[F_CG_RED0 + k], st.epoch);
-                const size_t off = (st.epoch & 1) ? red_off1 : red_off0;
+                double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+                if (lane < pe.n) {
+                    cg_wait_flag(&flags[F_CG_RED0 + lane], st.epoch);
+                    const size_t off = (st.epoch & 1) ? red_off1 : red_off0;
+                    const double* v = reinterpret_cast<const double*>(pe.arena + off + (size_t)lane * 128 * 8) + kCgSlot;
+                    v0 = __ldcg(v); v1 = __ldcg(v + 1); v2 = __ldcg(v + 2);
+                }
+                __syncwarp();
                 gam = rr = del = 0.0;
                 for (int k = 0; k < pe.n; k++) {  // rank order: bitwise identical on every rank
-                    const double* v = reinterpret_cast<const double*>(pe.arena + off + (size_t)k * 128 * 8) + kCgSlot;
-                    gam += __ldcg(v); rr += __ldcg(v + 1); del += __ldcg(v + 2);
+                    gam += __shfl_sync(0xffffffffu, v0, k); rr += __shfl_sync(0xffffffffu, v1, k); del += __shfl_sync(0xffffffffu, v2, k);
                 }
             } else {
                 gam = cg->sums[0]; rr = cg->sums[1]; del = cg->sums[2];
             }
-            if (blockIdx.x == 0) cg_trace(pe, st.epoch + 1, 1);
-            double a, b;
-            if (st.first != 0.0) { b = 0.0; a = gam / del; }
-            else { b = gam / st.gam_prev; a = gam / (del - b * gam / st.alpha_prev); }
-            sh[0] = a; sh[1] = b;
-            if (blockIdx.x == 0) {
-                cg->st[par ^ 1].gam_prev = gam; cg->st[par ^ 1].alpha_prev = a; cg->st[par ^ 1].first = 0.0;
-                cg->st[par ^ 1].epoch = st.epoch + 1;
-                cg->out[0] = gam; cg->out[1] = rr; cg->out[2] = del; cg->out[3] = a;
+            if (lane == 0) {
+                if (blockIdx.x == 0) cg_trace(pe, st.epoch + 1, 1);
+                double a, b;
+                if (st.first != 0.0) { b = 0.0; a = gam / del; }
+                else { b = gam / st.gam_prev; a = gam / (del - b * gam / st.alpha_prev); }
+                sh[0] = a; sh[1] = b;
+                if (blockIdx.x == 0) {
+                    cg->st[par ^ 1].gam_prev = gam; cg->st[par ^ 1].alpha_prev = a; cg->st[par ^ 1].first = 0.0;
+                    cg->st[par ^ 1].epoch = st.epoch + 1;
+                    cg->out[0] = gam; cg->out[1] = rr; cg->out[2] = del; cg->out[3] = a;
+                }
             }
         }
         __syncthreads();
