@@ -34,6 +34,8 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const doubl
             long long plane, double* __restrict__ upart, const __grid_constant__ CgPeers pe, size_t red_off0, size_t red_off1) {
     __shared__ double red[32];
     __shared__ double sh[2];
+    pdl_wait();               // everything below reads what the preceding S kernel (and the U before it) wrote
+    pdl_launch_dependents();  // the S kernel's CTAs may take the SMs as this grid's blocks retire
     const CgState st = cg->st[par];
     double alpha = 0.0, beta = 0.0;
     if (MODE == 1) {
@@ -165,11 +167,18 @@ int cg_update(tob_ctx_impl* c, const LevelGrid& g, CgDev* cg, int par, int mode,
     nb = std::min(nb, resident_grid(c, (const void*)k_cg_update<0, 0>, kFlatThreads, g.own_len));
     const long long o = g.own_off;
     const size_t r0 = peers.n > 1 ? cg_red_off(peers.n, 0, 0) : 0, r1 = peers.n > 1 ? cg_red_off(peers.n, 1, 0) : 0;
-#define TOB_CG_ARGS cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, g.own_len, g.pstride, upart, peers, r0, r1
-    if (mode == 0) k_cg_update<0, 0><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
-    else if (xmode == 1) k_cg_update<1, 1><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
-    else if (xmode == 2) k_cg_update<1, 2><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
-    else k_cg_update<1, 0><<<nb, kFlatThreads, 0, c->stream>>>(TOB_CG_ARGS);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nb); cfg.blockDim = dim3(kFlatThreads); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && mode == 1) ? 1 : 0;
+    const long long own_len = g.own_len, pstride = g.pstride;
+#define TOB_CG_ARGS cg, par, x + o, r + o, u + o, w + o, p + o, s + o, dinv + o, own_len, pstride, upart, peers, r0, r1
+    if (mode == 0) TOB_CUDA(cudaLaunchKernelEx(&cfg, k_cg_update<0, 0>, TOB_CG_ARGS));
+    else if (xmode == 1) TOB_CUDA(cudaLaunchKernelEx(&cfg, k_cg_update<1, 1>, TOB_CG_ARGS));
+    else if (xmode == 2) TOB_CUDA(cudaLaunchKernelEx(&cfg, k_cg_update<1, 2>, TOB_CG_ARGS));
+    else TOB_CUDA(cudaLaunchKernelEx(&cfg, k_cg_update<1, 0>, TOB_CG_ARGS));
 #undef TOB_CG_ARGS
     c->launches++;
     TOB_KERNEL_CHECK();

@@ -43,6 +43,17 @@ struct CgPeers {  // per-launch description of the neighbourhood (by value in th
     unsigned long long* trace = nullptr;
     int trace_cap = 0;
 };
+// Programmatic dependent launch (TOB_PDL=1, off by default) for the U/S pair: the next kernel of the pair is made resident while
+// the current one drains and parks at pdl_wait().  Measured on 2 GPUs (cfg2): the S -> U gap shrinks 2.2 -> 1.7 us but the U -> S
+// hand-over does not (an S CTA needs a whole SM, so it cannot start before the U blocks of that SM are gone) and the iteration is
+// 1-2 % slower -- kept as a switch, not as the default.  Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+    static const bool on = getenv("TOB_PDL") && atoi(getenv("TOB_PDL")) != 0;
+    return on;
+}
+
 __device__ __forceinline__ void cg_trace(const CgPeers& pe, unsigned long long epoch, int k) {
     if (pe.trace) {
         unsigned long long t;

@@ -570,8 +570,12 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
     const int nactive = jb - ja + 1;
     const bool rowactive = (j >= ja) && (j <= jb) && (ty < NCOMP);
 
+    if (EPI == EPI_CGDOT) pdl_launch_dependents();  // the next U kernel may become resident as CTAs retire (it parks at its own wait)
     if (z0 < z1) {
         if (tid == 0) {
+            // programmatic dependent launch: this grid may have started while the U kernel was draining -- thread 0 waits for its
+            // completion here; every other thread's first global access lies behind the block barrier below
+            if (EPI == EPI_CGDOT) pdl_wait();
             if (EPI == EPI_CGDOT && (P.pe.n > 1 || P.pe.trace)) {
                 // the boundary planes of the operand are stored into my ghost planes by the neighbours' U kernels: only the
                 // chunks that read a ghost plane wait (system-scope acquire of the epoch flag in my arena)
@@ -908,7 +912,17 @@ static int launch_zm(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op
         kp.k[rho][1] = make_double2(b[2], b[4]);
         kp.k[rho][2] = make_double2(b[5], b[8]);
     }
-    kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, kp, P);
+    if (EPI == EPI_CGDOT && pdl_enabled()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, gy, nch); cfg.blockDim = dim3(32 * TY); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        TOB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmU, tmE, kp, P));
+    } else {
+        kern<<<dim3(gx, gy, nch), 32 * TY, L::TOTAL, c->stream>>>(tmU, tmE, kp, P);
+    }
     c->launches++;
     TOB_KERNEL_CHECK();
     if (nparts) *nparts = (EPI == EPI_DOT || EPI == EPI_RESID || EPI == EPI_CGDOT) ? gx * gy * nch : 0;
