@@ -134,13 +134,13 @@ k_cg_update(CgDev* __restrict__ cg, int par, double* __restrict__ x, const doubl
         if (pe.n > 1 || pe.trace) {
             __syncthreads();
             if (threadIdx.x == 0) {
-                __threadfence_system();  // one fence per block, behind the barrier (cumulative over the block's stores)
+                fence_acq_rel_sys();  // one fence per block, behind the barrier (cumulative over the block's stores)
                 const unsigned int done = atomicAdd(&cg->ucounter, 1u) + 1u;
                 if (done == (unsigned int)nbnd) {
                     cg->ucounter = 0u;
-                    __threadfence_system();
-                    if (pe.rank > 0) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank - 1]) + F_CG_FROM_HI, e);
-                    if (pe.rank < pe.n - 1) cg_st_release_sys(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank + 1]) + F_CG_FROM_LO, e);
+                    fence_acq_rel_sys();  // tickets observed -> fence -> relaxed flag stores: one release pattern for both neighbours
+                    if (pe.rank > 0) st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank - 1]) + F_CG_FROM_HI, e);
+                    if (pe.rank < pe.n - 1) st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(pe.peer[pe.rank + 1]) + F_CG_FROM_LO, e);
                     cg_trace(pe, e, 2);
                 }
             }

@@ -54,6 +54,14 @@ inline bool pdl_enabled() {
     return on;
 }
 
+// System-scope release pattern with ONE fence: fence.acq_rel.sys followed by relaxed system-scope stores (PTX memory model: a
+// fence + relaxed store is a release pattern).  The first version used __threadfence_system() (MEMBAR.SC.SYS) and then a
+// st.release.sys per flag (each a MEMBAR.ALL.SYS + store): 3-4 system fences in series on the critical path of every iteration.
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 __device__ __forceinline__ void cg_trace(const CgPeers& pe, unsigned long long epoch, int k) {
     if (pe.trace) {
         unsigned long long t;

@@ -835,8 +835,8 @@ k_hex8_zm4(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUte
                 if (tid < P.pe.n) {
                     double* dst = reinterpret_cast<double*>(P.pe.peer[tid] + off) + kCgSlot;
                     dst[0] = s_sum[0]; dst[1] = s_sum[1]; dst[2] = s_sum[2];
-                    __threadfence_system();
-                    st_release_sys_u64(reinterpret_cast<unsigned long long*>(P.pe.peer[tid]) + F_CG_RED0 + P.pe.rank, e);
+                    fence_acq_rel_sys();  // sums -> fence -> relaxed flag store (one system fence instead of two)
+                    st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(P.pe.peer[tid]) + F_CG_RED0 + P.pe.rank, e);
                 }
                 if (tid == 0) cg_trace(P.pe, e, 5);
             }
