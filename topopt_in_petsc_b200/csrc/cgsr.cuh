@@ -23,7 +23,7 @@ struct CgState {  // ping-pong: U reads st[par], writes st[par ^ 1]
 struct CgDev {
     CgState st[2];
     double sums[3];         // single rank: r.u, r.r, w.u of the last (U, S) pair
-    unsigned int ucounter;  // "last CTA" tickets of U (halo flags) and S (reduction)
+    unsigned int ucounter;  // tickets: the boundary blocks of U (the last one raises the neighbours' flags), the CTAs of S (reduction)
     unsigned int scounter;
     double out[4];          // for the host: r.u, r.r, w.u, alpha
 };

@@ -532,11 +532,12 @@ int hex8_tc32b(tob_ctx_impl* c, const LevelGrid& g, const float* dB, const float
 // ELEMENTS (the window with lower corner node I), so one tile computes all 24 outputs of the element at once:
 //     D[e][0..23] = KE * u_e            4 MMAs of M 128, N 32, K 8 per 128 elements  (instead of 32 of N 16)
 // still without any gather (the A operand is the overlapping-descriptor view of the raw nodal planes).  What comes back is
-// per ELEMENT, so the epilogue scales the row by the element's modulus and sums the eight element contributions of a node
-// through a transposed shared-memory buffer (24 conflict-free stores per element thread, 24 conflict-free loads per node
-// thread, no atomics); contributions to the plane above are carried in registers to the next layer.  Tiles overlap by one
-// element (7 x 15 complete nodes per 8 x 16 elements).  The MMAs of layer L + 1 are issued before the node sums of layer L,
-// so the tensor pipe works under the epilogue.
+// per ELEMENT, so the epilogue scales the row by the element's modulus and sums the eight element contributions of a node:
+// the four elements of a layer around a node are lane - 1 (x), lane - 8 (y) and lane - 9 of the same warp, so the sums are
+// warp shuffles; only the element row that crosses a warp boundary goes through shared memory (YM 2, the default; YM 0 / 1 keep
+// the earlier transposed-buffer forms for A/B).  Contributions to the plane above are carried in registers to the next layer.
+// Tiles overlap by one element (7 x 15 complete nodes per 8 x 16 elements).  The MMAs of layer L + 1 are issued before the node
+// sums of layer L (two TMEM accumulators), so the tensor pipe works under the epilogue.  8 CTAs per SM (the TMEM limit).
 // =========================================================================================================================
 constexpr int T3_EX = 8, T3_EY = 16;               // elements per tile layer (= UMMA M)
 constexpr int T3_PX = T3_EX + 1, T3_PY = T3_EY + 1;
