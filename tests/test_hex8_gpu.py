@@ -308,7 +308,14 @@ def test_iteration1_compliance_cfg2_vs_cpu_reference_solver():
         res[name] = (fx, dfdx.copy(), st.iterations)
         phys.close()
     ctx.close()
-    cr = cpu_ref.CpuRef(*shape, nthreads=os.cpu_count())
+    # physical cores, at most 32: the C restatement is memory-bound (8 cores: 50 s for this solve) and its barriers spin -- with one
+    # thread per *logical* CPU of a 64-core box the same solve took ten minutes
+    try:
+        import psutil
+        ncores = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except ImportError:
+        ncores = max(1, (os.cpu_count() or 2) // 2)
+    cr = cpu_ref.CpuRef(*shape, nthreads=min(32, ncores))
     cr.assemble(x)
     cr.mg_setup(4)
     U, its, rel, _ = cr.fgmres_mg(rtol=1e-8, maxits=200)  # compliance error is second order in the residual
