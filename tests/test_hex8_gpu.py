@@ -290,8 +290,9 @@ def test_spmv_parity_cfg2_size(oracle, dens):
 def test_iteration1_compliance_cfg2_vs_cpu_reference_solver():
     """Iteration-1 compliance of BASELINE configs[1] (192x96x96, uniform 0.12): the product's Jacobi-PCG (default kernel,
     L2 hints and CUDA-graphed iterations on) and its multigrid-PCG, both to 1e-10, against the C restatement of the
-    reference's FGMRES + Galerkin-PCMG solver on the assembled CSR matrix (oracle/c/cpu_ref.c) to 1e-8.
-    Compliance error is second order in the residual -> 1e-8 relative."""
+    reference's FGMRES + Galerkin-PCMG solver on the assembled CSR matrix (oracle/c/cpu_ref.c), also to 1e-10: FGMRES
+    minimises the residual, not the energy error, so the compliance f.u is only FIRST order in it (measured: rtol 1e-8 leaves
+    1.4e-8 .. 5e-8 relative in fx depending on the thread count, rtol 1e-10 leaves 7e-11).  Checked to 1e-8 relative."""
     import cpu_ref
     from topopt_in_petsc_b200 import Context, LinearElasticity, solver_opts
     shape = (193, 97, 97)
@@ -318,8 +319,8 @@ def test_iteration1_compliance_cfg2_vs_cpu_reference_solver():
     cr = cpu_ref.CpuRef(*shape, nthreads=min(32, ncores))
     cr.assemble(x)
     cr.mg_setup(4)
-    U, its, rel, _ = cr.fgmres_mg(rtol=1e-8, maxits=200)  # compliance error is second order in the residual
-    assert rel <= 1e-8
+    U, its, rel, _ = cr.fgmres_mg(rtol=1e-10, maxits=200)  # 13-15 iterations, about a minute on 8 cores
+    assert rel <= 1e-10
     fx0, gx0, df0, _ = cr.objective(U, x)
     cr.close()
     print(f"cfg2 iteration 1: cpu fx={fx0:.12g} ({its} FGMRES its), jacobi {res['jacobi'][0]:.12g} ({res['jacobi'][2]} its), "
