@@ -948,6 +948,7 @@ int hex8_spmv(tob_ctx_impl* c, const LevelGrid& g, const Hex8Operator& op, const
     // (192x96x96: 43 us vs 49 (same tile, __syncthreads) / 57-61 (32x8 tiles); 256^3: 0.325 ms vs 0.385 / 0.362-0.391)
     int kernel = a.kernel == SPMV_AUTO ? SPMV_ZM16U4 : a.kernel;  // gen 2 (profiles/r02_spmv_probe_*.txt)
     if (a.mask_in && kernel != SPMV_NAIVE) TOB_FAIL("z-march kernels expect a pre-masked input (N.u); mask the input first");
+    if (a.epi == EPI_CHEB && !a.a1f) TOB_FAIL("Chebyshev epilogue: the fp32 copy of the inverse diagonal (SpmvArgs::a1f) is missing");
     if (kernel == SPMV_NAIVE) {
         if (a.epi != EPI_Y) TOB_FAIL("naive SpMV kernel supports only the plain epilogue");
         dim3 grid(div_up(g.nxn, 128), g.nyn, g.zl_own1() - g.zl_own0());
