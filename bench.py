@@ -416,20 +416,50 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def pick_cpu_threads(c, cores, nlv):
+    """Thread count of the CPU arm: the restated solver is memory-bound and its smoothers are block-local (one OpenMP thread = one
+    PETSc rank), so "all cores" is not always the fastest choice (a 64-core box ran one FGMRES iteration of cfg2 in 2.6 s with 64
+    threads and about half of that with 32).  Time two FGMRES iterations of the actual problem for cores, cores/2, cores/4 and
+    keep the fastest; TOB_REF_THREADS overrides.  Any failure falls back to all cores."""
+    if os.environ.get("TOB_REF_THREADS"):
+        return max(1, int(os.environ["TOB_REF_THREADS"])), {"forced": True}
+    cands = sorted({n for n in (cores, cores // 2, cores // 4) if n >= 4}, reverse=True) or [cores]
+    if len(cands) == 1:
+        return cands[0], {}
+    timings = {}
+    try:
+        import cpu_ref
+        x = np.full(c["nex"] * c["ney"] * c["nez"], c["volfrac"])
+        for n in cands:
+            cr = cpu_ref.CpuRef(c["nex"] + 1, c["ney"] + 1, c["nez"] + 1, xc=c["xc"], nu=c["nu"], nthreads=n)
+            try:
+                cr.assemble(x, c["Emin"], c["Emax"], c["penal"])
+                cr.mg_setup(nlv)
+                _, _, _, sec = cr.fgmres_mg(rtol=1e-30, maxits=2)
+                timings[n] = float(sec)
+            finally:
+                cr.close()
+        best = min(timings, key=timings.get)
+        return best, {"seconds_for_2_fgmres_iterations": {str(k): round(v, 3) for k, v in timings.items()}}
+    except Exception as e:  # calibration is a convenience, never a reason to lose the arm
+        return cores, {"calibration_failed": repr(e)[:200]}
+
+
 def cpu_whole_steps(c, steps, warmup, budget_s):
-    """Whole design iterations of the reference's algorithm on all host cores (oracle/cpu_design_loop.py).  Runs `warmup`
+    """Whole design iterations of the reference's algorithm on the host cores (oracle/cpu_design_loop.py; thread count = the
+    fastest of cores, cores/2, cores/4 for this problem on this box, see pick_cpu_threads).  Runs `warmup`
     untimed and up to `steps` timed iterations, stopping early (after at least one) when the next one would not fit into
     `budget_s` seconds of wall clock.  Nothing is extrapolated."""
     if c["filter"] != 1 or c["bc"] != "cantilever":
         return {"unavailable": "the CPU restatement covers the reference's own problem (cantilever, cone filter) only"}
     # threads pinned to cores, memory first-touched by the threads that use it (the solver is memory-bound)
-    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PROC_BIND", "spread")  # (fewer threads than cores: spread them over the sockets' memory channels)
     os.environ.setdefault("OMP_PLACES", "cores")
     import cpu_design_loop as cd
-    cores = host_cores()
+    nlv = min(4, gmg_levels(c))  # -nlvls 4 is the reference default (TopOpt.cc:116)
+    cores, calib = pick_cpu_threads(c, host_cores(), nlv)  # (outside the timed steps and outside their budget)
     t_begin = time.perf_counter()
     dx = (c["xc"][1] - c["xc"][0]) / c["nex"]
-    nlv = min(4, gmg_levels(c))  # -nlvls 4 is the reference default (TopOpt.cc:116)
     L = cd.CpuDesignLoop(c["nex"], c["ney"], c["nez"], volfrac=c["volfrac"], penal=c["penal"], Emin=c["Emin"], Emax=c["Emax"],
                          rmin=c["rmin_cells"] * dx, nlvls=nlv, rtol=c["rtol"], Xmin=c["Xmin"], Xmax=c["Xmax"],
                          movlim=c["movlim"], nthreads=cores, xc=c["xc"], nu=c["nu"])
@@ -445,7 +475,8 @@ def cpu_whole_steps(c, steps, warmup, budget_s):
     L.close()
     tot = sum(r["seconds"]["total"] for r in recs)
     parts = {k: float(np.mean([r["seconds"][k] for r in recs])) for k in recs[0]["seconds"]}
-    return {"value": len(recs) / tot, "unit": "design iterations/s", "cores": cores, "kind": "port",
+    return {"value": len(recs) / tot, "unit": "design iterations/s", "cores": cores, "host_cores": host_cores(), "thread_calibration": calib,
+            "kind": "port",
             "sample": f"{len(recs)} WHOLE design iteration(s) (design iterations {recs[0]['itr']}..{recs[-1]['itr']} from the uniform "
                       f"start) of {c['desc'].split(',')[0]}: CSR re-assembly + Galerkin PtAP set-up ({nlv} levels) + FGMRES(100) "
                       "rtol 1e-5 warm-started with a multiplicative V-cycle, GMRES(4)+SOR smoothers, GMRES(30)+SOR coarse solve "
